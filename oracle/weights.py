@@ -1,0 +1,84 @@
+"""Deterministic synthetic BEATs weights (numpy).  Test infrastructure -- see oracle/__init__.py.
+
+There is no network for checkpoints, so tests / bench use random-init weights of the named
+architecture.  Keys and shapes are exactly the reference `beats_model.Model.state_dict()`
+(dumped live), so the same dict loads into the reference module
+(`load_state_dict`, used by tests/golden/make_golden.py) and into `avex_b200`'s model.
+
+init="reference": the reference's init *distributions* (backbone.py:59-62,109-122,426-436,577-600;
+                  torch defaults for patch_embedding / post_extract_proj): biases 0, LayerNorm (1,0).
+init="perturbed": same weight scales, but non-zero biases, non-trivial LayerNorm affine, grep_a != 1 and
+                  an O(1) relative-position table, so that every parameter influences the output and
+                  indexing bugs are visible.  Used for the parity goldens.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .beats_encoder import BeatsDims
+
+
+def make_beats_weights(dims: BeatsDims = BeatsDims(), seed: int = 1, init: str = "perturbed") -> dict:
+    rs = np.random.RandomState(seed)
+    pert = init == "perturbed"
+
+    def normal(shape, std):
+        return (rs.standard_normal(shape) * std).astype(np.float32)
+
+    def uniform(shape, bound):
+        return rs.uniform(-bound, bound, size=shape).astype(np.float32)
+
+    def bias(n, std=0.02):
+        return normal((n,), std) if pert else np.zeros((n,), np.float32)
+
+    def ln(n):
+        if pert:
+            return (1.0 + normal((n,), 0.1)).astype(np.float32), normal((n,), 0.05)
+        return np.ones((n,), np.float32), np.zeros((n,), np.float32)
+
+    C, E, Ff, H = dims.embed, dims.patch_embed, dims.ffn, dims.heads
+    d = C // H
+    W: dict = {}
+    p2 = dims.patch * dims.patch
+    W["backbone.post_extract_proj.weight"] = uniform((C, E), 1.0 / math.sqrt(E))
+    W["backbone.post_extract_proj.bias"] = uniform((C,), 1.0 / math.sqrt(E))
+    W["backbone.patch_embedding.weight"] = uniform((E, 1, dims.patch, dims.patch), 1.0 / math.sqrt(p2))
+    W["backbone.layer_norm.weight"], W["backbone.layer_norm.bias"] = ln(E)
+    K, G = dims.conv_pos, dims.conv_groups
+    v = normal((C, C // G, K), math.sqrt(4.0 / (K * C)))  # backbone.py:59-61
+    W["backbone.encoder.pos_conv.0.bias"] = bias(C)
+    g = np.sqrt((v.astype(np.float64) ** 2).sum(axis=(0, 1), keepdims=True)).astype(np.float32)
+    if pert:
+        g = (g * (1.0 + normal((1, 1, K), 0.1))).astype(np.float32)
+    W["backbone.encoder.pos_conv.0.parametrizations.weight.original0"] = g
+    W["backbone.encoder.pos_conv.0.parametrizations.weight.original1"] = v
+    W["backbone.encoder.layer_norm.weight"], W["backbone.encoder.layer_norm.bias"] = ln(C)
+    beta = math.pow(8 * dims.layers, -0.25)  # backbone.py:112
+    table = normal((dims.num_buckets, H), 1.0 if pert else 0.02)
+    for li in range(dims.layers):
+        p = f"backbone.encoder.layers.{li}"
+        W[f"{p}.self_attn.grep_a"] = (
+            (1.0 + normal((1, H, 1, 1), 0.2)) if pert else np.ones((1, H, 1, 1), np.float32)
+        ).astype(np.float32)
+        W[f"{p}.self_attn.relative_attention_bias.weight"] = table  # shared storage, backbone.py:100-103
+        xav = math.sqrt(2.0 / (C + C))
+        W[f"{p}.self_attn.k_proj.weight"] = normal((C, C), xav)
+        W[f"{p}.self_attn.k_proj.bias"] = bias(C)
+        W[f"{p}.self_attn.v_proj.weight"] = normal((C, C), xav * beta)
+        W[f"{p}.self_attn.v_proj.bias"] = bias(C)
+        W[f"{p}.self_attn.q_proj.weight"] = normal((C, C), xav)
+        W[f"{p}.self_attn.q_proj.bias"] = bias(C)
+        W[f"{p}.self_attn.out_proj.weight"] = normal((C, C), xav * beta)
+        W[f"{p}.self_attn.out_proj.bias"] = bias(C)
+        W[f"{p}.self_attn.grep_linear.weight"] = normal((8, d), 0.2 if pert else 0.02)
+        W[f"{p}.self_attn.grep_linear.bias"] = bias(8, 0.2)
+        W[f"{p}.self_attn_layer_norm.weight"], W[f"{p}.self_attn_layer_norm.bias"] = ln(C)
+        xf = math.sqrt(2.0 / (C + Ff)) * beta
+        W[f"{p}.fc1.weight"] = normal((Ff, C), xf)
+        W[f"{p}.fc1.bias"] = bias(Ff)
+        W[f"{p}.fc2.weight"] = normal((C, Ff), xf)
+        W[f"{p}.fc2.bias"] = bias(C)
+        W[f"{p}.final_layer_norm.weight"], W[f"{p}.final_layer_norm.bias"] = ln(C)
+    return W

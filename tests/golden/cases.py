@@ -1,0 +1,57 @@
+"""Seeded inputs for the golden vectors (shared by make_golden.py and the tests).
+
+Inputs are regenerated at test time (they are seeded and the image is identical on the GPU box);
+REPORT.json stores a sha of every input so that a silent RNG change is caught.
+The fbank cases are the six inputs of the reference's tests/unittests/test_batched_fbank.py:52-80
+plus the 6 x 1 s sine batch of tests/integration/test_official_models_output_regression.py:135-156.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def _randn(seed: int, *shape) -> np.ndarray:
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).numpy()
+
+
+def sine_batch() -> np.ndarray:
+    t = np.arange(16000, dtype=np.float64) / 16000.0
+    rows = [a * np.sin(2 * np.pi * f * t) for f in (220.0, 440.0, 880.0) for a in (0.8, 0.9)]
+    return np.stack(rows).astype(np.float32)
+
+
+def fbank_cases() -> dict:
+    t = torch.linspace(0, 1, 16000)
+    return {
+        "sine440_1s": (torch.sin(2 * torch.pi * 440 * t).unsqueeze(0).numpy(), 128),
+        "randn42_4x1s": (_randn(42, 4, 16000), 128),
+        "randn7_1x10s": (_randn(7, 1, 160000), 128),
+        "randn0_quarter_s": (_randn(0, 1, 4000), 128),
+        "randn99_2x2s_mel64": (_randn(99, 2, 32000), 64),
+        "randn99_2x2s_mel256": (_randn(99, 2, 32000), 256),
+        "sine_batch_6x1s": (sine_batch(), 128),
+        "gauss0p1_2x5s": (_randn(1234, 2, 80000) * np.float32(0.1), 128),
+        "ragged_401": (_randn(5, 3, 401), 128),
+        "ragged_16123": (_randn(6, 2, 16123), 128),
+    }
+
+
+def eat_case() -> np.ndarray:
+    return _randn(11, 2, 48000) * np.float32(0.3) + np.float32(0.05)
+
+
+def beats_cases() -> dict:
+    mask = np.zeros((2, 32000), dtype=bool)
+    mask[1, 19200:] = True  # second clip padded after 1.2 s
+    return {
+        # 2-layer model, fast on CPU; every hooked layer kept
+        "L2_2x1s": dict(layers=2, wseed=1, wav=_randn(21, 2, 16000) * np.float32(0.1), keep_hooks=[0, 1, 2]),
+        # key-padding mask path (production Collater always passes one)
+        "L2_2x2s_mask": dict(layers=2, wseed=2, wav=_randn(22, 2, 32000) * np.float32(0.1), mask=mask, keep_hooks=[0, 2]),
+        # full 12-layer BEATs-base, 2 s
+        "L12_1x2s": dict(layers=12, wseed=3, wav=_randn(23, 1, 32000) * np.float32(0.1), keep_hooks=[0, 1, 6, 12]),
+        # BASELINE.json configs[0]: batch 1 x 5 s (N = 248 tokens, not a multiple of 64/128)
+        "L12_1x5s": dict(layers=12, wseed=4, wav=_randn(1234, 1, 80000) * np.float32(0.1), keep_hooks=[0, 12]),
+    }
