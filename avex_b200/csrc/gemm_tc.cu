@@ -1,0 +1,251 @@
+// gemm_tc.cu -- persistent, warp-specialised bf16 GEMM on the sm_100a tensor cores.
+//
+//   D[M,N] = epilogue(A[M,K] @ W[N,K]^T)      (A, W bf16 K-major; fp32 accumulation in TMEM)
+//
+// Replaces every nn.Linear on the BEATs path (backbone.py:531-533 q/k/v, :572 out_proj, :365-370 fc1/fc2,
+// beats.py:350 patch-embed as im2col GEMM, :359 post_extract_proj) and the elementwise ops that follow them
+// (bias, exact GELU, DeepNorm residual `residual * alpha + x`, backbone.py:360,:372), fused in the epilogue.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer : cp.async.bulk.tensor 128x64 (A) + 256x64 (W) bf16 tiles, 128B swizzle, 4-stage ring
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma 128x256x16 (cta_group::1), commits to mbarriers
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 from TMEM -> registers -> per-warp smem transposition ->
+//                              coalesced 16-byte global loads (bias/residual) and stores
+//   TMEM: 512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roofline: dense bf16 tensor pipe; algorithmic FLOPs = 2*M*N*K.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace avexk {
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int STG_PITCH = 36;                                  // floats per staged row (32 + 4 pad)
+constexpr int STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;         // 4608
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 256;
+constexpr int NTHREADS = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;
+  int gelu;
+  float* raw_out;
+  const float* residual;
+  float res_scale;
+  void* out;
+  long long ldo;
+  int out_bf16;
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): exact-GELU (modules.py:191-200) well inside bf16 rounding.
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|v|/sqrt2)
+  return 0.5f * v * (1.0f + copysignf(e, v));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_base = smem;
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (g.M + BM - 1) / BM, n_blocks = (g.N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks, num_kb = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = stage_base + stage * STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          ptx::tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
+          ptx::tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(stage_base + stage * STAGE_BYTES);
+          const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
+    float* stg = stg_base + (warp - 2) * (32 * STG_PITCH);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const int row0 = m_blk * BM + quarter * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= g.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + c * 32, r);
+        ptx::tmem_ld_wait();
+        // lane owns one row: park its 32 columns, then re-read so that 8 lanes cover one 128-byte row segment
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        __syncwarp();
+        const int cc = col0 + (lane & 7) * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int grow = row0 + rr;
+          if (grow < g.M && cc < g.N) {
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + (lane & 7) * 4);
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (g.gelu) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
+            const size_t off = (size_t)grow * g.N + cc;
+            if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
+            if (g.residual != nullptr) {
+              const float4 rs = __ldg(reinterpret_cast<const float4*>(g.residual + off));
+              v.x = fmaf(g.res_scale, rs.x, v.x); v.y = fmaf(g.res_scale, rs.y, v.y);
+              v.z = fmaf(g.res_scale, rs.z, v.z); v.w = fmaf(g.res_scale, rs.w, v.w);
+            }
+            if (g.out != nullptr) {
+              const size_t oo = (size_t)grow * g.ldo + cc;
+              if (g.out_bf16) {
+                uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + oo) = pk;
+              } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + oo) = v;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, int gelu,
+                     float* raw_out, const float* residual, float res_scale, void* out, long long ldo, int out_bf16,
+                     cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  GemmArgs g{M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16};
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, g);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long long lda, const void* W, long long ldw, int M,
+                   int N, int K) {
+  int rc = make_tmap_2d_bf16(map_a, A, M, K, lda, BM, BK);
+  if (rc) return rc;
+  return make_tmap_2d_bf16(map_b, W, N, K, ldw, BN, BK);
+}
+
+}  // namespace avexk
+
+extern "C" int avexk_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                               const float* bias, int gelu, float* raw_out, const float* residual, float res_scale, void* out,
+                               long long ldo, int out_bf16, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(A && W && (out || raw_out), "avexk_gemm_bf16: null operand");
+  AVEXK_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % 64 == 0 && N % 16 == 0, "avexk_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
+  AVEXK_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0 && (out == nullptr || (ldo >= N && ldo % 8 == 0)),
+                  "avexk_gemm_bf16: bad leading dimensions");
+  if (M == 0) return AVEXK_OK;
+  CUtensorMap ma, mb;
+  int rc = gemm_make_maps(&ma, &mb, A, lda, W, ldw, M, N, K);
+  if (rc) return rc;
+  return gemm_bf16_launch(ma, mb, M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16,
+                          reinterpret_cast<cudaStream_t>(stream));
+}

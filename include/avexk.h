@@ -1,0 +1,161 @@
+/*
+ * avexk.h -- C ABI of libavexk.so: the B200 (sm_100a) kernels behind avex's embedding hot path.
+ *
+ * This is the drop-in boundary one step below the reference's Python plugin classes
+ * (avex/models/beats_model.py:72 `Model`, avex/models/efficientnet.py:22 `Model`): it replaces the torch
+ * ops those classes reach through avex/models/beats/{beats,backbone}.py and avex/data/audio_utils.py.
+ * The reference has no FFI of its own (pure Python); the binding a maintainer adds is the ctypes stub in
+ * avex_b200/_lib.py, described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every `const float* x` / `void* out` below is a DEVICE pointer unless the
+ *    name ends in `_host`.  The caller (torch) owns all buffers and keeps them alive until the stream work is done.
+ *  - every entry point is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing on the
+ *    hot path (handles allocate at create / load time) and returns 0 on success, a negative AVEXK_E* code on
+ *    failure; `avexk_last_error()` returns a thread-local message.
+ *  - handles are thread-compatible, not thread-safe.
+ */
+#ifndef AVEXK_H
+#define AVEXK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVEXK_OK 0
+#define AVEXK_EINVAL (-1)  /* bad argument / unsupported shape */
+#define AVEXK_ECUDA (-2)   /* CUDA runtime / driver error       */
+#define AVEXK_ENOMEM (-3)  /* workspace too small               */
+
+const char* avexk_last_error(void);
+int avexk_version(void);
+/* number of kernel launches this library has enqueued since load (bench.py's `gpu_launches`). */
+long long avexk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Kaldi-style log-mel filterbank.
+ * Replaces `_BatchedFbank.forward` + the affine of `BEATs.preprocess`
+ *   (avex/models/beats/beats.py:120-163, :304-323) and, with window=hanning / prescale=1 / pad_to_frames=1024,
+ *   `EATAudioProcessor.__call__` (avex/models/eat/audio_processor.py:72-143).
+ * Geometry is fixed to the reference's: 16 kHz, 25 ms / 10 ms (400 / 160 samples), n_fft 512, 128 mel bins.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct avexk_fbank avexk_fbank_t;
+
+/* window_host[400] and mel_fb_host[257*128] (row-major [fft_bin][mel_bin]) are HOST arrays built by the caller
+ * with the reference's own fp32 formulas (beats.py:75, :82-118); the library derives the sparse mel table
+ * (<= 2 non-zeros per FFT bin) and double-precision twiddles and uploads them to the current device. */
+int avexk_fbank_create(const float* window_host, const float* mel_fb_host, avexk_fbank_t** out);
+void avexk_fbank_destroy(avexk_fbank_t* h);
+
+/* frames = 1 + (T - 400) / 160 (snip_edges, beats.py:136); 0 when T < 400. */
+int avexk_fbank_num_frames(int T);
+
+/* wav [B, T] fp32 with row stride `wav_stride` elements.  out [B, out_frames, 128] fp32.
+ *   out[b,f,m] = (log(max(mel, FLT_EPSILON)) - norm_mean) * norm_scale        (beats.py:163, :323)
+ * prescale: 32768 for BEATs (beats.py:322), 1 for EAT.  out_frames <= 0 means "num_frames(T)"; larger values
+ * zero-pad in the log-mel domain before normalisation, smaller truncate (eat/audio_processor.py:121-126).
+ * per_utt != 0: ignore norm_mean/scale and normalise each clip with its own mean and unbiased std,
+ *   (x - mu) / (2 sigma) (eat/audio_processor.py:132-135); needs stats_ws >= B * 2 doubles (device).
+ * out_bf16 != 0 stores bf16 instead of fp32. */
+int avexk_fbank_forward(const avexk_fbank_t* h, const float* wav, int B, int T, long long wav_stride, float prescale,
+                        float norm_mean, float norm_scale, int out_frames, int per_utt, double* stats_ws, void* out,
+                        int out_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Building blocks (each unit-testable against the oracle)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* D = epilogue(A @ W^T): A [M,K] bf16 row-major (lda), W [N,K] bf16 row-major (nn.Linear layout), fp32
+ * accumulation on the tcgen05 tensor cores (TMA-fed, accumulators in TMEM).
+ *   v = acc + bias[n]                                (bias may be NULL)
+ *   if gelu:      v = 0.5 v (1 + erf(v / sqrt 2))    (modules.py:191-200)
+ *   if raw_out:   raw_out[m,n] = v   (fp32; the tensor a forward hook on the Linear would see)
+ *   if residual:  v = v + res_scale * residual[m,n]  (fp32 residual; backbone.py:360, :372)
+ *   out[m,n] = v  as fp32 (out_bf16 == 0) or bf16    (out may be NULL when only raw_out is wanted)
+ * Requirements: K % 64 == 0, N % 16 == 0, all pointers 16-byte aligned, ld* % 8 == 0. */
+int avexk_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
+                    int gelu, float* raw_out, const float* residual, float res_scale, void* out, long long ldo,
+                    int out_bf16, void* stream);
+
+/* Row LayerNorm over the last dimension C (eps 1e-5): y = (x - mu) / sqrt(var + eps) * gamma + beta.
+ * x [M,C] fp32; writes out_f32 and / or out_bf16 (either may be NULL). */
+int avexk_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, float* out_f32,
+                    void* out_bf16, void* stream);
+
+/* Gated relative-position-bias attention (backbone.py:494-574), one launch for all (b, h).
+ * qkv [B*N, 3*H*64] bf16 (q | k | v, each head-major within H*64), as written by the fused QKV GEMM.
+ * gate_w [2,64], gate_b [2]: grep_linear rows pre-summed in groups of four (backbone.py:547-549);
+ * grep_a [H]; bias_vec [H, 2N-1] with bias_vec[h, (j-i)+N-1] = table[bucket(j-i), h] (backbone.py:475-492);
+ * key_pad [B,N] bytes (1 = padded key -> -inf) or NULL.  out [B*N, H*64] bf16 (token-major, ready for out_proj).
+ *   out_i = softmax_j(q_i.k_j / 8 + gate_i * bias[h, j-i] + pad_j) . v_j,  gate from UNscaled q. */
+int avexk_attention_gated(const void* qkv, int B, int N, int H, const float* gate_w, const float* gate_b,
+                          const float* grep_a, const float* bias_vec, const uint8_t* key_pad, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BEATs encoder (avex/models/beats/beats.py:325-382 + backbone.py:151-221), whole forward in one call.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct avexk_beats avexk_beats_t;
+
+typedef struct {
+  int layers;       /* 12  */
+  int embed;        /* 768 */
+  int ffn;          /* 3072 */
+  int heads;        /* 12  */
+  int patch_embed;  /* 512 */
+  int conv_pos;     /* 128 */
+  int conv_groups;  /* 16  */
+  float fbank_mean; /* 15.41663 */
+  float fbank_std;  /* 6.55582  */
+  float ln_eps;     /* 1e-5 */
+} avexk_beats_dims;
+
+/* fp32 DEVICE pointers in the reference's own layouts (state_dict names in comments). */
+typedef struct {
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b; /* self_attn.{q,k,v,out}_proj.{weight [C,C],bias}  */
+  const float *grep_w, *grep_b, *grep_a;                       /* self_attn.grep_linear.{weight [8,64],bias}, grep_a */
+  const float *ln1_w, *ln1_b;                                  /* self_attn_layer_norm                           */
+  const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;                  /* fc1 [Ff,C], fc2 [C,Ff]                          */
+  const float *ln2_w, *ln2_b;                                  /* final_layer_norm                               */
+} avexk_beats_layer_weights;
+
+typedef struct {
+  const float* patch_w;            /* backbone.patch_embedding.weight [E,1,16,16]                               */
+  const float *ln0_w, *ln0_b;      /* backbone.layer_norm [E]                                                   */
+  const float *proj_w, *proj_b;    /* backbone.post_extract_proj [C,E]                                          */
+  const float *posconv_g;          /* encoder.pos_conv.0.parametrizations.weight.original0 [1,1,K]              */
+  const float *posconv_v;          /* ...original1 [C, C/groups, K]                                             */
+  const float *posconv_b;          /* encoder.pos_conv.0.bias [C]                                               */
+  const float *enc_ln_w, *enc_ln_b;/* encoder.layer_norm [C]                                                    */
+  const float* rel_bias_table;     /* layers.0.self_attn.relative_attention_bias.weight [buckets, H]            */
+  const avexk_beats_layer_weights* layers; /* HOST array of `dims.layers` entries                              */
+} avexk_beats_weights;
+
+int avexk_beats_create(const avexk_beats_dims* dims, avexk_beats_t** out);
+void avexk_beats_destroy(avexk_beats_t* h);
+/* Packs bf16 copies (fused QKV [3C,C], weight-norm resolved pos-conv, gate rows pre-summed). Synchronises. */
+int avexk_beats_load_weights(avexk_beats_t* h, const avexk_beats_weights* w, void* stream);
+
+/* tokens for T samples: 8 * floor(num_frames(T) / 16). */
+int avexk_beats_num_tokens(int T);
+size_t avexk_beats_workspace_bytes(const avexk_beats_t* h, int B, int T);
+
+/* wav [B,T] fp32 (row stride wav_stride).  key_pad [B,N] bytes or NULL (already reduced from the sample mask by
+ * the host, beats.py:283-302).  bias_vec [H, 2N-1] fp32, host-precomputed from rel_bias_table with the
+ * reference's bucket function (backbone.py:438-492).
+ * out       [B,N,C] fp32 final features (may be NULL when only pooled is wanted)
+ * hook_out  HOST array of layers+1 DEVICE pointers (NULL entry = not materialised):
+ *             [0]   post_extract_proj output [B,N,C] (rows of padded tokens zeroed, as the reference's in-place
+ *                   `x[padding_mask] = 0` makes a hook see them, backbone.py:169-170)
+ *             [i+1] raw fc2 output of block i [B,N,C]   (beats_model.py:206-227)
+ * pooled    [B,C] fp32 mean over tokens (masked mean when key_pad has padded tokens, beats_model.py:269-275); may be NULL. */
+int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, int T, long long wav_stride,
+                        const avexk_fbank_t* fbank, const uint8_t* key_pad, const float* bias_vec, float* out,
+                        float* const* hook_out, float* pooled, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVEXK_H */
