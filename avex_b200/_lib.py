@@ -59,6 +59,8 @@ SIGNATURES = {
     "avexk_last_error": (C.c_char_p, []),
     "avexk_version": (_i, []),
     "avexk_launch_count": (_ll, []),
+    "avexk_profile_enable": (None, [_i]),
+    "avexk_profile_read": (_i, [_i, C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "avexk_fbank_create": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "avexk_fbank_destroy": (None, [_vp]),
     "avexk_fbank_num_frames": (_i, [_i]),
@@ -66,6 +68,8 @@ SIGNATURES = {
     "avexk_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _ll, _i, _vp]),
     "avexk_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "avexk_attention_gated": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "avexk_posconv_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "avexk_posconv": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "avexk_beats_create": (_i, [C.POINTER(BeatsDims), C.POINTER(_vp)]),
     "avexk_beats_destroy": (None, [_vp]),
     "avexk_beats_load_weights": (_i, [_vp, C.POINTER(BeatsWeights), _vp]),

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 
@@ -20,6 +21,26 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-kernel CUDA-event profiler (bench.py roofline leg; off on the hot path) -----------------------
+namespace {
+struct ProfRec { int kid; double work; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(cudaStream_t st, int kid, double work) {
+  if (!g_prof_on) return;
+  ProfRec r{kid, work, nullptr, nullptr};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, st);
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -37,3 +58,24 @@ int num_sms() {
 extern "C" const char* avexk_last_error(void) { return avexk::g_err; }
 extern "C" int avexk_version(void) { return 100; }
 extern "C" long long avexk_launch_count(void) { return avexk::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" void avexk_profile_enable(int on) {
+  for (auto& r : avexk::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  avexk::g_prof.clear();
+  avexk::g_prof_on = on != 0;
+}
+extern "C" int avexk_profile_read(int kid, long long* launches, double* total_ms, double* total_work) {
+  long long n = 0;
+  double ms = 0.0, work = 0.0;
+  for (auto& r : avexk::g_prof) {
+    if (r.kid != kid) continue;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) { avexk::set_error("avexk_profile_read: event sync failed"); return AVEXK_ECUDA; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms += t; work += r.work; ++n;
+  }
+  if (launches) *launches = n;
+  if (total_ms) *total_ms = ms;
+  if (total_work) *total_work = work;
+  return AVEXK_OK;
+}

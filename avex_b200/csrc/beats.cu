@@ -1,0 +1,262 @@
+// beats.cu -- BEATs encoder forward as one C-ABI call: enqueues every kernel of the path on the caller's stream.
+//
+// Mirrors avex/models/beats/beats.py:325-382 (front end) and backbone.py:151-221, :350-373 (12 post-LN DeepNorm
+// blocks).  Data layout in HBM (M = B*N token rows, batch-major; C = 768):
+//   x    fp32 [M,C]   residual stream (never rounded to bf16: SURVEY.md section 7, bf16 tolerance analysis)
+//   xb   bf16 [M,C]   copy of x feeding the next tensor-core GEMM (written by the LayerNorm kernel)
+//   qkv  bf16 [M,3C]  fused q|k|v projection, token-major; attention reads 128-byte head rows straight from it
+//   att  bf16 [M,C]   attention output, token-major (the reference's permute+contiguous never happens)
+//   h    bf16 [M,4C]  GELU(fc1)
+//   tmp  fp32 [M,C]   pre-LayerNorm sums (GEMM epilogue output)
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+struct avexk_beats {
+  avexk_beats_dims d;
+  bool loaded = false;
+  std::vector<void*> allocs;
+  // packed weights (device)
+  __nv_bfloat16 *patch_w = nullptr, *proj_w = nullptr, *posconv_w = nullptr;
+  float *ln0_w, *ln0_b, *proj_b, *posconv_b, *enc_ln_w, *enc_ln_b;
+  struct Layer {
+    __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
+    float *qkv_b, *o_b, *fc1_b, *fc2_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b, *gate_w, *gate_b, *grep_a;
+  };
+  std::vector<Layer> layers;
+};
+
+namespace avexk {
+namespace {
+
+template <typename T>
+int dev_alloc(avexk_beats* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return AVEXK_ECUDA;
+  }
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return AVEXK_OK;
+}
+
+int copy_f32(avexk_beats* h, float** dst, const float* src, size_t n, cudaStream_t st) {
+  int rc = dev_alloc(h, dst, n);
+  if (rc) return rc;
+  AVEXK_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return AVEXK_OK;
+}
+
+int pack_bf16_w(avexk_beats* h, __nv_bfloat16** dst, const float* src, size_t n, cudaStream_t st) {
+  int rc = dev_alloc(h, dst, n);
+  if (rc) return rc;
+  return launch_f32_to_bf16(src, *dst, (long long)n, st);
+}
+
+struct Carver {
+  char* p;
+  size_t left;
+  bool ok = true;
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (bytes > left) { ok = false; return nullptr; }
+    T* r = reinterpret_cast<T*>(p);
+    p += bytes;
+    left -= bytes;
+    return r;
+  }
+};
+
+struct Plan {
+  int B, T, F, N;
+  long long M;
+};
+
+size_t workspace_bytes(const avexk_beats_dims& d, int B, int T) {
+  const long long F = avexk_fbank_num_frames(T), N = 8 * (F / 16), M = (long long)B * N;
+  const long long C = d.embed, E = d.patch_embed, Ff = d.ffn, G = d.conv_groups;
+  auto al = [](long long b) { return (size_t)((b + 255) & ~255LL); };
+  size_t s = 0;
+  s += al((long long)B * F * 128 * 4);  // fbank
+  s += al(M * 768 * 2);                 // patch operand [hi|lo|hi]
+  s += al(M * E * 4);                   // patch-embed out
+  s += al(M * E * 3 * 2);               // LN(512) bf16 [hi|lo|hi]
+  s += al(M * C * 4);                   // x0 (hook 0) when the caller gives no buffer
+  s += al(M * G * 64 * 2);              // group-padded pos-conv operand
+  s += al(M * C * 4);                   // x
+  s += al(M * C * 2);                   // xb
+  s += al(M * 3 * C * 2);               // qkv
+  s += al(M * C * 2);                   // att
+  s += al(M * Ff * 2);                  // h
+  s += al(M * C * 4);                   // tmp
+  return s + 4096;
+}
+
+}  // namespace
+}  // namespace avexk
+
+extern "C" int avexk_beats_num_tokens(int T) { return 8 * (avexk_fbank_num_frames(T) / 16); }
+
+extern "C" int avexk_beats_create(const avexk_beats_dims* dims, avexk_beats_t** out) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(dims && out, "avexk_beats_create: null argument");
+  const avexk_beats_dims& d = *dims;
+  AVEXK_CHECK_ARG(d.layers >= 1 && d.heads >= 1 && d.embed == d.heads * 64, "BEATs kernels need head_dim 64 (embed=%d heads=%d)", d.embed, d.heads);
+  AVEXK_CHECK_ARG(d.embed % 128 == 0 && d.patch_embed % 128 == 0 && d.ffn % 64 == 0 && d.embed <= 1024 && d.patch_embed <= 1024,
+                  "unsupported widths embed=%d patch_embed=%d ffn=%d", d.embed, d.patch_embed, d.ffn);
+  AVEXK_CHECK_ARG(d.conv_pos == 128 && d.embed / d.conv_groups == 48, "pos-conv kernel needs 128 taps and 48 channels per group");
+  auto* h = new avexk_beats();
+  h->d = d;
+  h->layers.resize(d.layers);
+  *out = h;
+  return AVEXK_OK;
+}
+
+extern "C" void avexk_beats_destroy(avexk_beats_t* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int avexk_beats_load_weights(avexk_beats_t* h, const avexk_beats_weights* w, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(h && w && w->layers, "avexk_beats_load_weights: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->loaded = false;
+  const avexk_beats_dims& d = h->d;
+  const size_t C = d.embed, E = d.patch_embed, Ff = d.ffn, G = d.conv_groups, K = d.conv_pos, cg = C / G;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  // front end in 3-term split bf16 (K tripled): [hi|hi|lo] weights against [hi|lo|hi] activations
+  TRY(dev_alloc(h, &h->patch_w, E * 256 * 3));
+  TRY(launch_f32_to_bf16_split3(w->patch_w, h->patch_w, (int)E, 256, st));
+  TRY(copy_f32(h, &h->ln0_w, w->ln0_w, E, st));
+  TRY(copy_f32(h, &h->ln0_b, w->ln0_b, E, st));
+  TRY(dev_alloc(h, &h->proj_w, C * E * 3));
+  TRY(launch_f32_to_bf16_split3(w->proj_w, h->proj_w, (int)C, (int)E, st));
+  TRY(copy_f32(h, &h->proj_b, w->proj_b, C, st));
+  TRY(copy_f32(h, &h->posconv_b, w->posconv_b, C, st));
+  TRY(copy_f32(h, &h->enc_ln_w, w->enc_ln_w, C, st));
+  TRY(copy_f32(h, &h->enc_ln_b, w->enc_ln_b, C, st));
+  float* nrm = nullptr;
+  TRY(dev_alloc(h, &nrm, K));
+  TRY(dev_alloc(h, &h->posconv_w, C * K * 64));
+  TRY(launch_posconv_pack(w->posconv_v, w->posconv_g, (int)C, (int)cg, (int)K, nrm, h->posconv_w, st));
+  for (int li = 0; li < d.layers; ++li) {
+    const avexk_beats_layer_weights& s = w->layers[li];
+    avexk_beats::Layer& L = h->layers[li];
+    TRY(dev_alloc(h, &L.qkv_w, 3 * C * C));
+    TRY(launch_f32_to_bf16(s.q_w, L.qkv_w, (long long)(C * C), st));
+    TRY(launch_f32_to_bf16(s.k_w, L.qkv_w + C * C, (long long)(C * C), st));
+    TRY(launch_f32_to_bf16(s.v_w, L.qkv_w + 2 * C * C, (long long)(C * C), st));
+    TRY(dev_alloc(h, &L.qkv_b, 3 * C));
+    AVEXK_CUDA(cudaMemcpyAsync(L.qkv_b, s.q_b, C * 4, cudaMemcpyDeviceToDevice, st));
+    AVEXK_CUDA(cudaMemcpyAsync(L.qkv_b + C, s.k_b, C * 4, cudaMemcpyDeviceToDevice, st));
+    AVEXK_CUDA(cudaMemcpyAsync(L.qkv_b + 2 * C, s.v_b, C * 4, cudaMemcpyDeviceToDevice, st));
+    TRY(pack_bf16_w(h, &L.o_w, s.o_w, C * C, st));
+    TRY(copy_f32(h, &L.o_b, s.o_b, C, st));
+    TRY(pack_bf16_w(h, &L.fc1_w, s.fc1_w, Ff * C, st));
+    TRY(copy_f32(h, &L.fc1_b, s.fc1_b, Ff, st));
+    TRY(pack_bf16_w(h, &L.fc2_w, s.fc2_w, C * Ff, st));
+    TRY(copy_f32(h, &L.fc2_b, s.fc2_b, C, st));
+    TRY(copy_f32(h, &L.ln1_w, s.ln1_w, C, st));
+    TRY(copy_f32(h, &L.ln1_b, s.ln1_b, C, st));
+    TRY(copy_f32(h, &L.ln2_w, s.ln2_w, C, st));
+    TRY(copy_f32(h, &L.ln2_b, s.ln2_b, C, st));
+    TRY(copy_f32(h, &L.grep_a, s.grep_a, d.heads, st));
+    TRY(dev_alloc(h, &L.gate_w, 128));
+    TRY(dev_alloc(h, &L.gate_b, 2));
+    TRY(launch_gate_pack(s.grep_w, s.grep_b, L.gate_w, L.gate_b, st));
+  }
+#undef TRY
+  AVEXK_CUDA(cudaStreamSynchronize(st));
+  h->loaded = true;
+  return AVEXK_OK;
+}
+
+extern "C" size_t avexk_beats_workspace_bytes(const avexk_beats_t* h, int B, int T) {
+  if (!h || B <= 0 || T < 400) return 0;
+  return avexk::workspace_bytes(h->d, B, T);
+}
+
+extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, int T, long long wav_stride,
+                                   const avexk_fbank_t* fbank, const uint8_t* key_pad, const float* bias_vec, float* out,
+                                   float* const* hook_out, float* pooled, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(h && h->loaded, "avexk_beats_forward: weights not loaded");
+  AVEXK_CHECK_ARG(wav && fbank && bias_vec && workspace, "avexk_beats_forward: null argument");
+  AVEXK_CHECK_ARG(out || pooled || hook_out, "avexk_beats_forward: no output requested");
+  const avexk_beats_dims& d = h->d;
+  const int F = avexk_fbank_num_frames(T), N = avexk_beats_num_tokens(T);
+  AVEXK_CHECK_ARG(B > 0 && N > 0, "avexk_beats_forward: clip too short (B=%d T=%d -> %d tokens)", B, T, N);
+  const long long M = (long long)B * N;
+  AVEXK_CHECK_ARG(M < (1LL << 31), "avexk_beats_forward: too many token rows (%lld)", M);
+  AVEXK_CHECK_ARG(workspace_bytes >= avexk::workspace_bytes(d, B, T), "avexk_beats_forward: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int C = d.embed, E = d.patch_embed, Ff = d.ffn, G = d.conv_groups, H = d.heads;
+  const float alpha = powf(2.0f * (float)d.layers, 0.25f);  // backbone.py:306
+
+  Carver cw{reinterpret_cast<char*>(workspace), workspace_bytes};
+  float* fb = cw.take<float>((size_t)B * F * 128);
+  __nv_bfloat16* pa = cw.take<__nv_bfloat16>((size_t)M * 768);
+  float* pe = cw.take<float>((size_t)M * E);
+  __nv_bfloat16* peb = cw.take<__nv_bfloat16>((size_t)M * E * 3);
+  float* x0_ws = cw.take<float>((size_t)M * C);
+  __nv_bfloat16* xg = cw.take<__nv_bfloat16>((size_t)M * G * 64);
+  float* x = cw.take<float>((size_t)M * C);
+  __nv_bfloat16* xb = cw.take<__nv_bfloat16>((size_t)M * C);
+  __nv_bfloat16* qkv = cw.take<__nv_bfloat16>((size_t)M * 3 * C);
+  __nv_bfloat16* att = cw.take<__nv_bfloat16>((size_t)M * C);
+  __nv_bfloat16* hb = cw.take<__nv_bfloat16>((size_t)M * Ff);
+  float* tmp = cw.take<float>((size_t)M * C);
+  AVEXK_CHECK_ARG(cw.ok, "avexk_beats_forward: workspace carve failed");
+  float* x0 = (hook_out && hook_out[0]) ? hook_out[0] : x0_ws;
+
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  auto gemm = [&](const void* A, int K, const __nv_bfloat16* W, int Nn, const float* bias, int gelu, float* raw, const float* res,
+                  float rs, void* o, int obf) -> int {
+    CUtensorMap ma, mb;
+    int r = gemm_make_maps(&ma, &mb, A, K, W, K, (int)M, Nn, K);
+    if (r) return r;
+    return gemm_bf16_launch(ma, mb, (int)M, Nn, K, bias, gelu, raw, res, rs, o, Nn, obf, st);
+  };
+
+  // ---- front end: fbank -> patch embed -> LN -> post_extract_proj (beats.py:344-359) -----------------------------
+  TRY(avexk_fbank_forward(fbank, wav, B, T, wav_stride, 32768.0f, d.fbank_mean, 1.0f / (2.0f * d.fbank_std), 0, 0, nullptr, fb, 0, stream));
+  TRY(launch_patchify(fb, B, F, pa, st));
+  TRY(gemm(pa, 768, h->patch_w, E, nullptr, 0, nullptr, nullptr, 0.f, pe, 0));
+  TRY(launch_layernorm(pe, (int)M, E, h->ln0_w, h->ln0_b, d.ln_eps, nullptr, peb, st, 1));
+  TRY(gemm(peb, 3 * E, h->proj_w, C, h->proj_b, 0, nullptr, nullptr, 0.f, x0, 0));
+  // ---- encoder prologue: mask, pos-conv + GELU + residual, LN (backbone.py:169-177) ------------------------------
+  TRY(launch_group_pad(x0, key_pad, M, G, C / G, xg, st));
+  TRY(launch_posconv(xg, h->posconv_w, h->posconv_b, x0, tmp, B, N, G, C / G, d.conv_pos, st));
+  TRY(launch_layernorm(tmp, (int)M, C, h->enc_ln_w, h->enc_ln_b, d.ln_eps, x, xb, st));
+  // ---- 12 post-LN DeepNorm blocks (backbone.py:350-373) --------------------------------------------------------------
+  for (int li = 0; li < d.layers; ++li) {
+    const avexk_beats::Layer& L = h->layers[li];
+    const bool last = li == d.layers - 1;
+    TRY(gemm(xb, C, L.qkv_w, 3 * C, L.qkv_b, 0, nullptr, nullptr, 0.f, qkv, 1));
+    TRY(avexk_attention_gated(qkv, B, N, H, L.gate_w, L.gate_b, L.grep_a, bias_vec, key_pad, att, stream));
+    TRY(gemm(att, C, L.o_w, C, L.o_b, 0, nullptr, x, alpha, tmp, 0));
+    TRY(launch_layernorm(tmp, (int)M, C, L.ln1_w, L.ln1_b, d.ln_eps, x, xb, st));
+    TRY(gemm(xb, C, L.fc1_w, Ff, L.fc1_b, 1, nullptr, nullptr, 0.f, hb, 1));
+    float* raw = hook_out ? hook_out[li + 1] : nullptr;
+    TRY(gemm(hb, Ff, L.fc2_w, C, L.fc2_b, 0, raw, x, alpha, tmp, 0));
+    float* dst = (last && out) ? out : x;
+    TRY(launch_layernorm(tmp, (int)M, C, L.ln2_w, L.ln2_b, d.ln_eps, dst, last ? nullptr : xb, st));
+    if (last && pooled) {
+      // any_pad is decided on the host by the caller passing key_pad == NULL when nothing is padded
+      TRY(launch_mean_pool(dst, key_pad, key_pad != nullptr, B, N, C, pooled, st));
+    }
+  }
+#undef TRY
+  return AVEXK_OK;
+}

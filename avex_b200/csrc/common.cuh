@@ -44,6 +44,12 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 
 int num_sms();
 
+// kernel ids of the optional event profiler (avexk_profile_*)
+enum { KID_FBANK = 0, KID_GEMM = 1, KID_ATTN = 2, KID_LAYERNORM = 3, KID_POSCONV = 4, KID_OTHER = 5 };
+bool prof_enabled();
+void prof_begin(cudaStream_t st, int kid, double work);
+void prof_end(cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -345,10 +345,12 @@ extern "C" int avexk_fbank_forward(const avexk_fbank_t* h, const float* wav, int
     ns = 1.f;
   }
   dim3 grid(ceil_div(Fout, FPC), B);
+  prof_begin(st, KID_FBANK, (double)B * (4.0 * T + (out_bf16 ? 2.0 : 4.0) * Fout * NMEL));
   if (out_bf16)
     fbank_kernel<true><<<grid, 256, SMEM_BYTES, st>>>(wav, wav_stride, T, F, Fout, prescale, nm, ns, h->tb, out, stats);
   else
     fbank_kernel<false><<<grid, 256, SMEM_BYTES, st>>>(wav, wav_stride, T, F, Fout, prescale, nm, ns, h->tb, out, stats);
+  prof_end(st);
   AVEXK_LAUNCH_CHECK();
   if (per_utt) {
     long long per_clip = (long long)Fout * NMEL;

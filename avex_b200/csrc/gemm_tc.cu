@@ -220,7 +220,9 @@ int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
   GemmArgs g{M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16};
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  prof_begin(st, KID_GEMM, 2.0 * M * N * K);
   gemm_bf16_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, g);
+  prof_end(st);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
 }

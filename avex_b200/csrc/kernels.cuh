@@ -1,0 +1,29 @@
+// kernels.cuh -- internal launch functions shared between translation units of libavexk.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace avexk {
+
+// gemm_tc.cu
+int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long long lda, const void* W, long long ldw, int M,
+                   int N, int K);
+int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, int gelu,
+                     float* raw_out, const float* residual, float res_scale, void* out, long long ldo, int out_bf16,
+                     cudaStream_t st);
+// elementwise.cu
+int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, float* out_f32,
+                     void* out_bf16, cudaStream_t st, int split3 = 0);
+int launch_f32_to_bf16_split3(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t st);
+int launch_patchify(const float* fb, int B, int F, __nv_bfloat16* A, cudaStream_t st);
+int launch_group_pad(float* x0, const uint8_t* key_pad, long long M, int G, int cg, __nv_bfloat16* xg, cudaStream_t st);
+int launch_mean_pool(const float* x, const uint8_t* key_pad, int any_pad, int B, int N, int C, float* out, cudaStream_t st);
+int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
+int launch_posconv_pack(const float* v, const float* g, int C, int cg, int K, float* nrm_ws, __nv_bfloat16* W, cudaStream_t st);
+int launch_gate_pack(const float* w, const float* b, float* gw, float* gb, cudaStream_t st);
+// posconv.cu
+int launch_posconv(const __nv_bfloat16* xg, const __nv_bfloat16* Wpc, const float* bias, const float* x0, float* out, int B,
+                   int N, int G, int cg, int taps, cudaStream_t st);
+
+}  // namespace avexk

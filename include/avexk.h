@@ -35,6 +35,12 @@ int avexk_version(void);
 /* number of kernel launches this library has enqueued since load (bench.py's `gpu_launches`). */
 long long avexk_launch_count(void);
 
+/* Optional per-kernel timing with CUDA events on the launching stream (measurement only; adds two event records
+ * per launch while enabled).  kid: 0 fbank (work = algorithmic bytes), 1 gemm (FLOPs), 2 attention (FLOPs),
+ * 3 layernorm (bytes), 4 posconv (FLOPs), 5 other.  avexk_profile_read synchronises on the recorded events. */
+void avexk_profile_enable(int on);
+int avexk_profile_read(int kid, long long* launches, double* total_ms, double* total_work);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Kaldi-style log-mel filterbank.
  * Replaces `_BatchedFbank.forward` + the affine of `BEATs.preprocess`
@@ -93,6 +99,17 @@ int avexk_layernorm(const float* x, int M, int C, const float* gamma, const floa
  *   out_i = softmax_j(q_i.k_j / 8 + gate_i * bias[h, j-i] + pad_j) . v_j,  gate from UNscaled q. */
 int avexk_attention_gated(const void* qkv, int B, int N, int H, const float* gate_w, const float* gate_b,
                           const float* grep_a, const float* bias_vec, const uint8_t* key_pad, void* out, void* stream);
+
+/* Convolutional position embedding (backbone.py:52-68, :172-174; modules.py:67-94):
+ *   out = x0 + GELU(Conv1d(C, C, k=taps, pad=taps/2, groups)(x0 along tokens)[..., :N] + bias),  weight = g * v / ||v||_(0,1)
+ * x0 [B,N,C] fp32 -- rows with key_pad != 0 are zeroed IN PLACE first (backbone.py:169-170); weight_g [taps],
+ * weight_v [C, C/groups, taps] fp32 (the weight_norm parametrisation); out [B,N,C] fp32.  Packs the weights on
+ * every call (unit-test / building-block entry; avexk_beats_forward packs once at load).
+ * workspace >= avexk_posconv_workspace_bytes(B, N, C, groups, taps). */
+size_t avexk_posconv_workspace_bytes(int B, int N, int C, int groups, int taps);
+int avexk_posconv(float* x0, int B, int N, int C, int groups, int taps, const float* weight_g, const float* weight_v,
+                  const float* bias, const uint8_t* key_pad, float* out, void* workspace, size_t workspace_bytes,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BEATs encoder (avex/models/beats/beats.py:325-382 + backbone.py:151-221), whole forward in one call.

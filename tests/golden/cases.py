@@ -54,4 +54,7 @@ def beats_cases() -> dict:
         "L12_1x2s": dict(layers=12, wseed=3, wav=_randn(23, 1, 32000) * np.float32(0.1), keep_hooks=[0, 1, 6, 12]),
         # BASELINE.json configs[0]: batch 1 x 5 s (N = 248 tokens, not a multiple of 64/128)
         "L12_1x5s": dict(layers=12, wseed=4, wav=_randn(1234, 1, 80000) * np.float32(0.1), keep_hooks=[0, 12]),
+        # the reference's own init distributions (zero biases, LayerNorm (1,0)): the setting BASELINE.json's
+        # tolerances (cos >= 0.999, max-abs <= 2e-2 in bf16) were calibrated on
+        "L12_1x10s_refinit": dict(layers=12, wseed=5, init="reference", wav=_randn(1234, 1, 160000) * np.float32(0.1), keep_hooks=[0, 1, 12]),
     }

@@ -153,7 +153,7 @@ def build_ref_beats(layers: int, W: dict):
 def gen_beats():
     for cname, case in cases.beats_cases().items():
         dims = OE.BeatsDims(layers=case["layers"])
-        W = make_beats_weights(dims, seed=case["wseed"], init="perturbed")
+        W = make_beats_weights(dims, seed=case["wseed"], init=case.get("init", "perturbed"))
         model = build_ref_beats(case["layers"], W)
         wav = case["wav"]
         mask = case.get("mask")

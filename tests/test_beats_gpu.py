@@ -1,0 +1,106 @@
+"""GPU: the fused BEATs forward behind the plugin surface, against the reference goldens (bf16 tolerances of
+BASELINE.json north_star: per-layer cosine >= 0.999 and max-abs <= 2e-2) and the numpy oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import beats_encoder as OE
+from oracle.weights import make_beats_weights
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _build(layers, wseed, return_features_only=True, num_classes=None):
+    from avex_b200 import plugin
+    from avex_b200.plugin import beats_model  # noqa: F401  (registers the "beats" class)
+
+    spec = plugin.ModelSpec(name="beats", device="cuda", init_config=dict(encoder_layers=layers, finetuned_model=True, dropout=0.0))
+    plugin.register_model(f"gpu_test_L{layers}", spec)
+    kw = {}
+    model = plugin.load_model(f"gpu_test_L{layers}", device="cuda", return_features_only=return_features_only, **kw).eval()
+    W = make_beats_weights(OE.BeatsDims(layers=layers), seed=wseed)
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}, strict=False)
+    assert not unexpected
+    assert all(k.startswith(("backbone.fbank.", "backbone.predictor.")) for k in missing), missing
+    return model, W
+
+
+def _cmp(name, got, ref, atol=2e-2, cos_min=0.999):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (name, got.shape, ref.shape)
+    err = np.abs(got - ref).max()
+    cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+    print(f"{name}: max_abs {err:.4e} cos {cos:.6f} (ref absmax {np.abs(ref).max():.3f})")
+    assert np.isfinite(got).all()
+    assert cos >= cos_min, (name, cos)
+    assert err <= atol, (name, err)
+
+
+@pytest.mark.parametrize("cname", list(cases.beats_cases()))
+def test_against_reference_golden(cname):
+    case = cases.beats_cases()[cname]
+    g = np.load(os.path.join(G, f"beats_{cname}.npz"))
+    model, W = _build(case["layers"], case["wseed"])
+    wav = torch.from_numpy(case["wav"]).cuda()
+    mask = torch.from_numpy(case["mask"]).cuda() if "mask" in case else None
+    with torch.no_grad():
+        feats = model(wav, mask)
+    _cmp(f"{cname}/final", feats.cpu().numpy(), g["final"])
+    names = model.register_hooks_for_layers(["all"])
+    assert names[0] == "backbone.post_extract_proj" and len(names) == case["layers"] + 1
+    hooks = model.extract_embeddings(wav, padding_mask=mask, aggregation="none")
+    assert len(hooks) == case["layers"] + 1
+    for li in case["keep_hooks"]:
+        _cmp(f"{cname}/hook{li}", hooks[li].cpu().numpy(), g[f"hook{li}"])
+    pooled = model.extract_embeddings(wav, padding_mask=mask, aggregation="mean")
+    _cmp(f"{cname}/pooled_hooks_mean", pooled.cpu().numpy(), g["pooled_hooks_mean"], atol=1e-2, cos_min=0.9999)
+    # hooks on a subset, by index, still work after the "all" registration
+    model.register_hooks_for_layers([0, -1])
+    two = model.extract_embeddings({"raw_wav": wav, "padding_mask": mask}, aggregation="mean")
+    assert two.shape == (wav.shape[0], 2 * 768)
+
+
+def test_classifier_mode_masked_mean_pool():
+    case = cases.beats_cases()["L2_2x2s_mask"]
+    from avex_b200 import plugin
+
+    model, W = _build(2, case["wseed"])
+    spec = plugin.get_model_spec("gpu_test_L2")
+    clf = plugin.build_model_from_spec(spec, "cuda", num_classes=10).to("cuda").eval()
+    clf.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}, strict=False)
+    wav = torch.from_numpy(case["wav"]).cuda()
+    mask = torch.from_numpy(case["mask"]).cuda()
+    with torch.no_grad():
+        logits = clf(wav, mask)
+        feats = model(wav, mask)
+    assert logits.shape == (2, 10) and torch.isfinite(logits).all()
+    orc = OE.beats_forward(W, case["wav"], case["mask"], OE.BeatsDims(layers=2))
+    pooled_ref = OE.mean_pool(orc["x"], orc["key_pad"])
+    want = pooled_ref @ clf.classifier.weight.detach().cpu().numpy().T + clf.classifier.bias.detach().cpu().numpy()
+    _cmp("classifier logits", logits.cpu().numpy(), want, atol=1e-2, cos_min=0.9999)
+    # all-False mask == no mask, bit-identical (verified property of the reference)
+    none = model(wav[:1], None)
+    allf = model(wav[:1], torch.zeros_like(mask[:1]))
+    assert torch.equal(none, allf)
+    assert feats.shape == (2, 96, 768)
+
+
+def test_batch_independence_and_full_size():
+    """BASELINE config #2 shape (256 x 10 s, N=496): a clip's embedding does not depend on its batch neighbours."""
+    model, W = _build(12, 3)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    wav = torch.randn(64, 160000, device="cuda", generator=g) * 0.1
+    with torch.no_grad():
+        full = model(wav)
+        one = model(wav[17:18])
+    assert full.shape == (64, 496, 768) and torch.isfinite(full).all()
+    assert torch.equal(full[17], one[0])
+    # oracle on one clip of the big batch (CPU, ~10 s)
+    orc = OE.beats_forward(W, wav[17:18].cpu().numpy(), None, OE.BeatsDims(layers=12))
+    _cmp("10s clip vs oracle", one.cpu().numpy(), orc["x"])

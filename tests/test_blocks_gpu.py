@@ -1,0 +1,167 @@
+"""GPU: every building block of the BEATs path through the C ABI, against fp32 torch / the numpy oracle."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import beats_encoder as OE
+from oracle import relpos as OR
+from oracle.weights import make_beats_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from avex_b200 import _lib
+
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc, lib):
+    assert rc == 0, lib.avexk_last_error().decode()
+
+
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 256, 256), (77, 512, 256), (300, 768, 512), (1000, 2304, 768),
+    (513, 768, 3072), (4096, 3072, 768), (129, 48 * 16, 768), (20000, 768, 768),
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_plain_fp32_out(lib, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _check(lib.avexk_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), 0, None, None, 0.0,
+                               out.data_ptr(), N, 0, _stream()), lib)  # fmt: skip
+    ref = A.float() @ W.float().T + bias
+    err = (out - ref).abs().max().item()
+    assert torch.isfinite(out).all()
+    assert err <= 2e-3, f"max abs err {err}"
+
+
+def test_gemm_epilogues(lib):
+    M, N, K = 777, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = A.float() @ W.float().T + bias
+    # bias + raw store + scaled residual, fp32 out (out_proj / fc2 epilogue)
+    out = torch.empty(M, N, device="cuda")
+    raw = torch.empty(M, N, device="cuda")
+    _check(lib.avexk_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), 0, raw.data_ptr(), res.data_ptr(),
+                               2.2133638, out.data_ptr(), N, 0, _stream()), lib)  # fmt: skip
+    assert (raw - ref).abs().max().item() <= 2e-3
+    assert (out - (ref + 2.2133638 * res)).abs().max().item() <= 3e-3
+    # bias + exact GELU, bf16 out (fc1 epilogue)
+    outb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _check(lib.avexk_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), 1, None, None, 0.0,
+                               outb.data_ptr(), N, 1, _stream()), lib)  # fmt: skip
+    gref = torch.nn.functional.gelu(ref)
+    assert (outb.float() - gref).abs().max().item() <= 2e-2
+    assert ((outb.float() - gref).abs() <= 8e-3 * gref.abs() + 2e-3).all()
+    # no bias, bf16 out
+    _check(lib.avexk_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, None, 0, None, None, 0.0,
+                               outb.data_ptr(), N, 1, _stream()), lib)  # fmt: skip
+    assert ((outb.float() - (ref - bias)).abs() <= 8e-3 * (ref - bias).abs() + 2e-3).all()
+
+
+def test_gemm_rejects_bad_shapes(lib):
+    A = torch.zeros(8, 100, device="cuda", dtype=torch.bfloat16)
+    assert lib.avexk_gemm_bf16(A.data_ptr(), 100, A.data_ptr(), 100, 8, 16, 100, None, 0, None, None, 0.0, A.data_ptr(), 16, 1, _stream()) != 0
+    assert b"unsupported shape" in lib.avexk_last_error()
+
+
+@pytest.mark.parametrize("M,Cw", [(1, 768), (9, 512), (1000, 768), (333, 1024), (64, 128)])
+def test_layernorm(lib, M, Cw):
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = torch.randn(M, Cw, device="cuda", generator=g) * 3 + 1
+    w = torch.randn(Cw, device="cuda", generator=g)
+    b = torch.randn(Cw, device="cuda", generator=g)
+    o32 = torch.empty_like(x)
+    o16 = torch.empty(M, Cw, device="cuda", dtype=torch.bfloat16)
+    _check(lib.avexk_layernorm(x.data_ptr(), M, Cw, w.data_ptr(), b.data_ptr(), 1e-5, o32.data_ptr(), o16.data_ptr(), _stream()), lib)
+    ref = torch.nn.functional.layer_norm(x, (Cw,), w, b, 1e-5)
+    assert (o32 - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()) * 4
+    assert torch.equal(o16, o32.to(torch.bfloat16))
+
+
+def _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, key_pad):
+    d = 64
+    q, k, v = [t.reshape(B, N, H, d).permute(0, 2, 1, 3).float() for t in qkv.split(H * d, dim=1)]
+    gl = q @ gw.T + gb  # [B,H,N,2]
+    gate = torch.sigmoid(gl)
+    g1 = gate[..., 0:1] * (gate[..., 1:2] * ga.view(1, H, 1, 1) - 1.0) + 2.0
+    idx = (torch.arange(N, device="cuda")[None, :] - torch.arange(N, device="cuda")[:, None]) + N - 1
+    s = q @ k.transpose(-1, -2) * 0.125 + g1 * bias_vec[:, idx][None]
+    if key_pad is not None:
+        s = s.masked_fill(key_pad[:, None, None, :].bool(), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * d)
+
+
+@pytest.mark.parametrize("B,N,H,pad", [(2, 48, 12, False), (1, 248, 12, False), (3, 96, 4, True), (2, 496, 2, False), (1, 700, 1, True)])
+def test_attention_gated(lib, B, N, H, pad):
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = (torch.randn(B * N, 3 * H * 64, device="cuda", generator=g)).to(torch.bfloat16)
+    gw = torch.randn(2, 64, device="cuda", generator=g) * 0.2
+    gb = torch.randn(2, device="cuda", generator=g) * 0.2
+    ga = 1.0 + 0.2 * torch.randn(H, device="cuda", generator=g)
+    table = torch.randn(320, H, generator=torch.Generator().manual_seed(1))
+    bias_vec = torch.from_numpy(OR.bias_vector(table.numpy(), N)).cuda()
+    key_pad = None
+    if pad:
+        key_pad = torch.zeros(B, N, dtype=torch.uint8, device="cuda")
+        key_pad[-1, N // 2 + 3 :] = 1
+    out = torch.empty(B * N, H * 64, device="cuda", dtype=torch.bfloat16)
+    _check(lib.avexk_attention_gated(qkv.data_ptr(), B, N, H, gw.data_ptr(), gb.data_ptr(), ga.data_ptr(), bias_vec.data_ptr(),
+                                     key_pad.data_ptr() if pad else None, out.data_ptr(), _stream()), lib)  # fmt: skip
+    ref = _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, key_pad)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    assert err <= 2e-2, err  # P and the output are rounded to bf16
+    assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
+
+
+@pytest.mark.parametrize("B,N,pad", [(2, 48, False), (1, 248, False), (2, 131, True), (3, 496, False)])
+def test_posconv(lib, B, N, pad):
+    dims = OE.BeatsDims()
+    W = make_beats_weights(OE.BeatsDims(layers=1), seed=7)
+    Cw = 768
+    g = torch.Generator(device="cuda").manual_seed(N)
+    x0 = torch.randn(B, N, Cw, device="cuda", generator=g)
+    key_pad = None
+    if pad:
+        key_pad = torch.zeros(B, N, dtype=torch.uint8, device="cuda")
+        key_pad[0, N - 20 :] = 1
+    xin = x0.clone()
+    x_ref = x0.cpu().numpy().copy()
+    if pad:
+        x_ref[key_pad.cpu().numpy().astype(bool)] = 0
+    ref = x_ref + OE.pos_conv(x_ref, W, dims)
+    wg = torch.from_numpy(W["backbone.encoder.pos_conv.0.parametrizations.weight.original0"]).cuda().contiguous()
+    wv = torch.from_numpy(W["backbone.encoder.pos_conv.0.parametrizations.weight.original1"]).cuda().contiguous()
+    bias = torch.from_numpy(W["backbone.encoder.pos_conv.0.bias"]).cuda()
+    need = lib.avexk_posconv_workspace_bytes(B, N, Cw, 16, 128)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    out = torch.empty_like(x0)
+    _check(lib.avexk_posconv(xin.data_ptr(), B, N, Cw, 16, 128, wg.data_ptr(), wv.data_ptr(), bias.data_ptr(),
+                             key_pad.data_ptr() if pad else None, out.data_ptr(), ws.data_ptr(), need, _stream()), lib)  # fmt: skip
+    got = out.cpu().numpy()
+    conv_scale = np.abs(ref - x_ref).max()
+    err = np.abs(got - ref).max()
+    print(f"posconv B={B} N={N}: max err {err:.3e} (conv magnitude {conv_scale:.3f})")
+    assert err <= 2e-2 * max(1.0, conv_scale)
+    if pad:
+        assert (xin[key_pad.bool()] == 0).all()

@@ -103,7 +103,7 @@ def test_beats_encoder(cname):
     g = np.load(os.path.join(G, f"beats_{cname}.npz"))
     assert _sha(case["wav"]) == REPORT["beats/" + cname]["input_sha"]
     dims = OE.BeatsDims(layers=case["layers"])
-    W = make_beats_weights(dims, seed=case["wseed"])
+    W = make_beats_weights(dims, seed=case["wseed"], init=case.get("init", "perturbed"))
     out = OE.beats_forward(W, case["wav"], case.get("mask"), dims)
     assert out["x"].shape == g["final"].shape
     np.testing.assert_allclose(out["x"], g["final"], atol=2e-4, rtol=1e-4)
@@ -114,3 +114,19 @@ def test_beats_encoder(cname):
     np.testing.assert_allclose(pooled, g["pooled_hooks_mean"], atol=1e-4, rtol=1e-4)
     if "key_pad" in g:
         assert (out["key_pad"] == g["key_pad"]).all()
+
+
+@pytest.mark.parametrize("cname", ["L2_2x2s_mask", "L12_1x2s"])
+def test_torch_flavour_of_the_oracle(cname):
+    """oracle/beats_torch.py (the timed CPU baseline) against the same reference goldens."""
+    import torch
+
+    from oracle import beats_torch as OT
+
+    case = cases.beats_cases()[cname]
+    g = np.load(os.path.join(G, f"beats_{cname}.npz"))
+    dims = OE.BeatsDims(layers=case["layers"])
+    W = make_beats_weights(dims, seed=case["wseed"], init=case.get("init", "perturbed"))
+    out = OT.beats_forward(OT.to_torch(W), torch.from_numpy(case["wav"]), case.get("mask"), dims)
+    np.testing.assert_allclose(out["x"].numpy(), g["final"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(out["hook0"].numpy(), g["hook0"], atol=1e-4, rtol=1e-4)
