@@ -6,11 +6,11 @@
 // beats.py:350 patch-embed as im2col GEMM, :359 post_extract_proj) and the elementwise ops that follow them
 // (bias, exact GELU, DeepNorm residual `residual * alpha + x`, backbone.py:360,:372), fused in the epilogue.
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0      TMA producer : cp.async.bulk.tensor 128x64 (A) + 256x64 (W) bf16 tiles, 128B swizzle, 4-stage ring
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma 128x256x16 (cta_group::1), commits to mbarriers
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 from TMEM -> registers -> per-warp smem transposition ->
-//                              coalesced 16-byte global loads (bias/residual) and stores
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 from TMEM -> registers -> per-warp smem transposition ->
+//                              coalesced 16-byte global stores; the fp32 residual is register-prefetched one chunk ahead
 //   TMEM: 512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Roofline: dense bf16 tensor pipe; algorithmic FLOPs = 2*M*N*K.
 #include "common.cuh"
@@ -22,10 +22,10 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int STG_PITCH = 36;                                  // floats per staged row (32 + 4 pad)
-constexpr int STG_BYTES_PER_WARP = 32 * STG_PITCH * 4;         // 4608
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP + 256;
-constexpr int NTHREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;                // 32 rows x 32 fp32, XOR-swizzled (no padding)
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 256;
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 
 struct GemmArgs {
   int M, N, K;
@@ -58,7 +58,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;
   float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * STG_BYTES_PER_WARP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
@@ -78,7 +78,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -137,11 +137,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
-    float* stg = stg_base + (warp - 2) * (32 * STG_PITCH);
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter; each owns four of the tile's eight 32-column chunks.  The fp32 residual of
+    // the NEXT chunk is prefetched into registers (8 independent 16-byte loads per lane) before the current chunk
+    // is processed, so HBM latency is overlapped instead of serialised behind the accumulator read.
+    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
+    float* stg = stg_base + ew * (32 * 32);
+    const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
+    const bool has_res = g.residual != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float4 res_next[8];
+    auto load_res = [&](int tile, int c, float4 (&dst)[8]) {
+      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      const int cc = n_blk * BN + c * 32 + csub * 4;
+      const int row0 = m_blk * BM + quarter * 32;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int grow = row0 + it * 4 + rsub;
+        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res && tile < num_tiles && grow < g.M && cc < g.N)
+          dst[it] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)grow * g.N + cc));
+      }
+    };
+    if (has_res) load_res(blockIdx.x, half * 4, res_next);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -149,47 +168,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       const int row0 = m_blk * BM + quarter * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = half * 4 + ci;
         const int col0 = n_blk * BN + c * 32;
-        if (col0 >= g.N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_addr + c * 32, r);
-        ptx::tmem_ld_wait();
-        // lane owns one row: park its 32 columns, then re-read so that 8 lanes cover one 128-byte row segment
+        float4 res_cur[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<uint4*>(stg + lane * STG_PITCH + 4 * i) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-        __syncwarp();
-        const int cc = col0 + (lane & 7) * 4;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+        for (int it = 0; it < 8; ++it) res_cur[it] = res_next[it];
+        if (has_res) {
+          if (ci < 3) load_res(tile, c + 1, res_next);
+          else load_res(tile + gridDim.x, half * 4, res_next);
+        }
+        if (col0 < g.N) {  // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_addr + c * 32, r);
+          ptx::tmem_ld_wait();
+          // lane owns one row: park its 32 columns (XOR-swizzled 16-byte slots), re-read so 8 lanes cover a 128 B row segment
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          const int grow = row0 + rr;
-          if (grow < g.M && cc < g.N) {
-            float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_PITCH + (lane & 7) * 4);
-            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-            if (g.gelu) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
-            const size_t off = (size_t)grow * g.N + cc;
-            if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
-            if (g.residual != nullptr) {
-              const float4 rs = __ldg(reinterpret_cast<const float4*>(g.residual + off));
-              v.x = fmaf(g.res_scale, rs.x, v.x); v.y = fmaf(g.res_scale, rs.y, v.y);
-              v.z = fmaf(g.res_scale, rs.z, v.z); v.w = fmaf(g.res_scale, rs.w, v.w);
-            }
-            if (g.out != nullptr) {
-              const size_t oo = (size_t)grow * g.ldo + cc;
-              if (g.out_bf16) {
-                uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + oo) = pk;
-              } else {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + oo) = v;
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          __syncwarp();
+          const int cc = col0 + csub * 4;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            const int grow = row0 + rr;
+            if (grow < g.M && cc < g.N) {
+              float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((csub ^ (rr & 7)) << 2));
+              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+              if (g.gelu) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
+              const size_t off = (size_t)grow * g.N + cc;
+              if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
+              if (has_res) {
+                v.x = fmaf(g.res_scale, res_cur[it].x, v.x); v.y = fmaf(g.res_scale, res_cur[it].y, v.y);
+                v.z = fmaf(g.res_scale, res_cur[it].z, v.z); v.w = fmaf(g.res_scale, res_cur[it].w, v.w);
+              }
+              if (g.out != nullptr) {
+                const size_t oo = (size_t)grow * g.ldo + cc;
+                if (g.out_bf16) {
+                  uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + oo) = pk;
+                } else {
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + oo) = v;
+                }
               }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
       ptx::tc_fence_before();

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _build(layers, wseed, return_features_only=True, num_classes=None):
+def _build(layers, wseed, return_features_only=True, num_classes=None, init="perturbed"):
     from avex_b200 import plugin
     from avex_b200.plugin import beats_model  # noqa: F401  (registers the "beats" class)
 
@@ -23,7 +23,7 @@ def _build(layers, wseed, return_features_only=True, num_classes=None):
     plugin.register_model(f"gpu_test_L{layers}", spec)
     kw = {}
     model = plugin.load_model(f"gpu_test_L{layers}", device="cuda", return_features_only=return_features_only, **kw).eval()
-    W = make_beats_weights(OE.BeatsDims(layers=layers), seed=wseed)
+    W = make_beats_weights(OE.BeatsDims(layers=layers), seed=wseed, init=init)
     missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}, strict=False)
     assert not unexpected
     assert all(k.startswith(("backbone.fbank.", "backbone.predictor.")) for k in missing), missing
@@ -46,7 +46,7 @@ def _cmp(name, got, ref, atol=2e-2, cos_min=0.999):
 def test_against_reference_golden(cname):
     case = cases.beats_cases()[cname]
     g = np.load(os.path.join(G, f"beats_{cname}.npz"))
-    model, W = _build(case["layers"], case["wseed"])
+    model, W = _build(case["layers"], case["wseed"], init=case.get("init", "perturbed"))
     wav = torch.from_numpy(case["wav"]).cuda()
     mask = torch.from_numpy(case["mask"]).cuda() if "mask" in case else None
     with torch.no_grad():
