@@ -1,0 +1,636 @@
+// attention_tc.cu -- fused multi-head attention on the sm_100a tensor cores (tcgen05 + TMEM), with BEATs' gated
+// relative-position bias applied in-tile.
+//
+// Replaces avex/models/beats/backbone.py:526-571: the [B,H,N,N] expansion of compute_bias, the gate
+// (grep_linear -> view(..,2,4).sum(-1) -> sigmoid -> gate_a*(gate_b*grep_a-1)+2, from UNscaled q), the materialised
+// `gate * position_bias` mask (3.0 GB fp32 per layer at B=256, N=496), the key-padding -inf mask, SDPA, and the
+// permute/contiguous that follows.  Nothing of size N^2 touches HBM: the Toeplitz bias is the [H, 2N-1] vector
+// bias[h, j-i+N-1], indexed inside the score tile and scaled by the per-row gate.
+//
+// Persistent kernel, one CTA per SM, 18 warps.  A work item is (clip, head, pair of 128-query tiles); both tiles of the
+// pair share every K/V tile that streams through a 3-stage TMA ring, and their softmax phases interleave so the tensor
+// pipe, the MUFU pipe and the TMA engine are all busy:
+//   warps 0..7   softmax group A, warps 8..15 softmax group B.  thread = (query row r = 32*(warp&3)+lane, column half
+//                ch = (warp>>2)&1).  Per 128-key tile a thread reads its 64 scores from TMEM (tcgen05.ld), adds scale /
+//                gated bias / mask, joins the row max with its partner through shared memory, exponentiates
+//                (ex2.approx) and writes the bf16 P row segment straight into the 128-byte-swizzled K-major layout the
+//                UMMA descriptor expects.  The running max is lazy (FA4-style): O in TMEM is only rescaled when the
+//                max grows by more than 2^8, which is exact after the final 1/l.
+//   warp 16      loaders: lane 0 streams 128-key K and V tiles (3-D tensor map: rows past the clip end are
+//                zero-filled by hardware), running ahead across work items; lane 1 loads the Q tiles.
+//   warp 17      MMA issuer: S_g = Q_g K^T (128x128x64, K-major operands) and O_g += P_g V (128x64x128, V consumed
+//                MN-major exactly as it lies in the qkv buffer -- no transposed copy), tcgen05.commit -> mbarriers.
+//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each), O_A @256, O_B @320 (fp32 128x64 each).
+// Roofline: MUFU (one ex2 per score: B*H*N^2 per layer) and FP32 issue, not the tensor pipe; see DESIGN.md section 4.
+#include <math.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace avexk {
+namespace {
+
+constexpr int BQ = 128, BKV = 128, HD = 64;
+constexpr int GROUP_WARPS = 8, GROUP_THREADS = 32 * GROUP_WARPS;
+constexpr int WARP_LOAD = 16, WARP_MMA = 17, NTHREADS = 32 * 18;
+constexpr int KV_STAGES = 3;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 domain: P stays below 2^8, exact after normalisation
+
+constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+// Four copies of the 255-entry bias window per tile, copy s shifted right by s floats so that every row can read
+// 16-byte aligned float4s.  Copy offsets (floats) are chosen so that the 8 lanes of each LDS.128 phase hit 8 distinct
+// 16-byte bank groups (offsets / 4 mod 8 = 0, 1, 3, 5).
+constexpr int WIN_FLOATS = 1056;
+constexpr int OFF_Q = 0;                                 // [2] tiles
+constexpr int OFF_KV = OFF_Q + 2 * TILE_BYTES;           // [KV_STAGES] x (K tile, V tile)
+constexpr int OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // [2 groups] x two 64-key atoms
+constexpr int OFF_TAB = OFF_P + 2 * 2 * TILE_BYTES;
+constexpr int TAB_WIN = 0;                               // [2][WIN_FLOATS] float
+constexpr int TAB_MASK = TAB_WIN + 2 * WIN_FLOATS * 4;  // [2][128] float
+constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] pass-A max / l, [2][128] gate
+constexpr int TAB_BYTES = TAB_PMAX + 1024 * 4 + 16;  // + one int: first tile with a valid key
+constexpr int OFF_GATEW = OFF_TAB + 2 * TAB_BYTES;  // [2][64] float + [2] bias
+constexpr int OFF_BAR = OFF_GATEW + 640;
+constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "attention_tc: shared memory budget");
+
+struct AttnTcArgs {
+  int B, N, H;
+  const float* gate_w;     // [2,64]
+  const float* gate_b;     // [2]
+  const float* grep_a;     // [H]
+  const float* bias_vec;   // [H, 2N-1]
+  const uint8_t* key_pad;  // [B,N] or null
+  __nv_bfloat16* out;      // [B*N, H*64]
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// explicit shared-space accesses (32-bit shared addresses): the carve-up below goes through an aligned byte offset, and
+// generic LD/ST on those pointers costs a long-scoreboard round trip
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns (small chunks keep the softmax threads under the 96-register budget that 18
+// warps per SM allow)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ int win_copy_offset(int s) { return s == 0 ? 0 : (s == 1 ? 260 : (s == 2 ? 524 : 788)); }
+
+// x = S * scale + gate * bias (+ mask): two scores per packed fp32x2 instruction.  Software pipeline per 16-column
+// chunk: the TMEM load of chunk c+1 and the window loads of chunk c+1 are in flight while chunk c is processed
+// (tcgen05.wait::ld waits for every outstanding load, so the next load is issued right after the wait).
+#define AVEXK_SCORE_QUAD(R, lo, hi)                                                                                       \
+  float2 lo = __ffma2_rn(make_float2(__uint_as_float(R[4 * k + 0]), __uint_as_float(R[4 * k + 1])), s2,                    \
+                         __fmul2_rn(g2, make_float2(w[k].x, w[k].y)));                                                    \
+  float2 hi = __ffma2_rn(make_float2(__uint_as_float(R[4 * k + 2]), __uint_as_float(R[4 * k + 3])), s2,                    \
+                         __fmul2_rn(g2, make_float2(w[k].z, w[k].w)));                                                    \
+  if (chunk < 3) w[k] = lds128(win_addr + ((chunk + 1) * 16 + k * 4) * 4);                                               \
+  if (MASKED) {                                                                                                           \
+    const float4 mk = lds128(mask_addr + (chunk * 16 + k * 4) * 4);                                                       \
+    lo = __fadd2_rn(lo, make_float2(mk.x, mk.y));                                                                         \
+    hi = __fadd2_rn(hi, make_float2(mk.z, mk.w));                                                                         \
+  }
+
+// Pass A (only on the first tile with a valid key): exact row max of this thread's 64 scores.
+template <bool MASKED>
+__device__ __forceinline__ float score_max(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale) {
+  float mx = -INFINITY;
+  const float2 g2 = make_float2(gate, gate), s2 = make_float2(qk_scale, qk_scale);
+  uint32_t ra[16], rb[16];
+  float4 w[4];
+  tmem_ld_32x16(taddr, ra);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = lds128(win_addr + k * 16);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    if (chunk < 3) tmem_ld_32x16(taddr + (chunk + 1) * 16, (chunk & 1) ? ra : rb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (chunk & 1) {
+        AVEXK_SCORE_QUAD(rb, lo, hi)
+        mx = fmaxf(fmaxf(mx, fmaxf(lo.x, lo.y)), fmaxf(hi.x, hi.y));
+      } else {
+        AVEXK_SCORE_QUAD(ra, lo, hi)
+        mx = fmaxf(fmaxf(mx, fmaxf(lo.x, lo.y)), fmaxf(hi.x, hi.y));
+      }
+    }
+    if (chunk < 3) ptx::tmem_ld_wait();
+  }
+  return mx;
+}
+
+// Pass B: stream the 64 scores once: p = 2^(min(x - m, 126)) -> bf16 -> swizzled P row segment; accumulates the row
+// sum and tracks the tile max (used to move the reference max for the NEXT tile).  Nothing is kept in registers.
+template <bool MASKED>
+__device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale,
+                                            float m_ref, uint32_t p_row, int rsw, float& mx_out, float& sum_out) {
+  float mx = -INFINITY;
+  const float2 g2 = make_float2(gate, gate), s2 = make_float2(qk_scale, qk_scale), nm2 = make_float2(-m_ref, -m_ref);
+  float2 sum2 = make_float2(0.f, 0.f);
+  uint32_t ra[16], rb[16];
+  float4 w[4];
+  tmem_ld_32x16(taddr, ra);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = lds128(win_addr + k * 16);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int chunk = 0; chunk < 4; ++chunk) {
+    if (chunk < 3) tmem_ld_32x16(taddr + (chunk + 1) * 16, (chunk & 1) ? ra : rb);
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 lo_, hi_;
+      if (chunk & 1) {
+        AVEXK_SCORE_QUAD(rb, lo, hi)
+        lo_ = lo; hi_ = hi;
+      } else {
+        AVEXK_SCORE_QUAD(ra, lo, hi)
+        lo_ = lo; hi_ = hi;
+      }
+      mx = fmaxf(fmaxf(mx, fmaxf(lo_.x, lo_.y)), fmaxf(hi_.x, hi_.y));
+      lo_ = __fadd2_rn(lo_, nm2);
+      hi_ = __fadd2_rn(hi_, nm2);
+      // the reference max may lag the true max (it moves between tiles): clamp so bf16 P cannot overflow
+      const float2 p0 = make_float2(ex2(fminf(lo_.x, 126.f)), ex2(fminf(lo_.y, 126.f)));
+      const float2 p1 = make_float2(ex2(fminf(hi_.x, 126.f)), ex2(fminf(hi_.y, 126.f)));
+      sum2 = __fadd2_rn(sum2, __fadd2_rn(p0, p1));
+      pk[2 * k] = pack_bf16(p0.x, p0.y);
+      pk[2 * k + 1] = pack_bf16(p1.x, p1.y);
+    }
+    sts128u(p_row + (((chunk * 2) ^ rsw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    sts128u(p_row + (((chunk * 2 + 1) ^ rsw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+    if (chunk < 3) ptx::tmem_ld_wait();
+  }
+  mx_out = mx;
+  sum_out = sum2.x + sum2.y;
+}
+
+struct Item {
+  int b, h, q0;
+  bool has_b;  // the pair's second tile holds at least one valid query row
+};
+__device__ __forceinline__ Item decode_item(int item, int npairs, int H, int N) {
+  Item it;
+  const int pair = item % npairs, bh = item / npairs;
+  it.h = bh % H;
+  it.b = bh / H;
+  it.q0 = pair * 2 * BQ;
+  it.has_b = it.q0 + BQ < N;
+  return it;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment (128B swizzle atoms); pointer arithmetic on the __shared__ array keeps the address space
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_a = ptx::smem_u32(smem);
+  unsigned char* sQ = smem + OFF_Q;
+  unsigned char* sKV = smem + OFF_KV;
+  unsigned char* sP = smem + OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;     // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [KV_STAGES]
+  uint64_t* kv_empty = bars + 8;   // [KV_STAGES]
+  uint64_t* s_full = bars + 12;    // [2]
+  uint64_t* p_full = bars + 14;    // [2]
+  uint64_t* o_full = bars + 16;    // [2]
+  uint64_t* o_free = bars + 18;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.N;
+  const int n_kv = (N + BKV - 1) / BKV;
+  const int npairs = (N + 2 * BQ - 1) / (2 * BQ);
+  const int n_items = a.B * a.H * npairs;
+
+  if (tid < 130) {  // gate weights [2][64] + bias [2] -> shared memory, once per CTA
+    const float v = tid < 128 ? __ldg(a.gate_w + tid) : __ldg(a.gate_b + tid - 128);
+    sts32(smem_a + OFF_GATEW + tid * 4, v);
+  }
+  if (warp == WARP_MMA) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&map_qkv);
+      for (int g = 0; g < 2; ++g) {
+        ptx::mbar_init(&q_full[g], 1);
+        ptx::mbar_init(&q_empty[g], GROUP_WARPS + 1);  // gate readers + the commit of the item's last S MMA
+        ptx::mbar_init(&s_full[g], 1);
+        ptx::mbar_init(&p_full[g], GROUP_WARPS);
+        ptx::mbar_init(&o_full[g], 1);
+        ptx::mbar_init(&o_free[g], GROUP_WARPS);
+      }
+      for (int s = 0; s < KV_STAGES; ++s) {
+        ptx::mbar_init(&kv_full[s], 1);
+        ptx::mbar_init(&kv_empty[s], 1);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == WARP_LOAD) {
+    if (lane == 0) {
+      // ===================== K/V loader =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(item, npairs, a.H, N);
+        const int col_k = (a.H + it.h) * HD, col_v = (2 * a.H + it.h) * HD;
+        for (int t = 0; t < n_kv; ++t) {
+          ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
+          unsigned char* dst = sKV + stage * 2 * TILE_BYTES;
+          ptx::mbar_arrive_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
+          ptx::tma_load_3d(dst, &map_qkv, &kv_full[stage], col_k, t * BKV, it.b);
+          ptx::tma_load_3d(dst + TILE_BYTES, &map_qkv, &kv_full[stage], col_v, t * BKV, it.b);
+          if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 1) {
+      // ===================== Q loader =====================
+      uint32_t cnt[2] = {0, 0};
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(item, npairs, a.H, N);
+        for (int g = 0; g < 2; ++g) {
+          if (g == 1 && !it.has_b) break;
+          ptx::mbar_wait(&q_empty[g], (cnt[g] & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&q_full[g], TILE_BYTES);
+          ptx::tma_load_3d(sQ + g * TILE_BYTES, &map_qkv, &q_full[g], it.h * HD, it.q0 + g * BQ, it.b);
+          ++cnt[g];
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ===================== MMA issuer =====================
+    // Event loop over the two query tiles of the item: whichever group has delivered P_g(t) gets S_g(t+1) issued first
+    // (it is on that group's critical path: its softmax warps are idle until it lands), then O_g += P_g(t) V(t).
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
+      constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD) | (1u << 16);  // B operand (V) is MN-major
+      uint32_t gt0 = 0;  // global index (over this CTA's items) of the item's first K/V tile
+      uint32_t items_g[2] = {0, 0}, tiles_g[2] = {0, 0};
+      auto issue_s = [&](int g, uint32_t gt) {
+        const int st = gt % KV_STAGES;
+        ptx::mbar_wait(&kv_full[st], (gt / KV_STAGES) & 1);  // returns at once if this phase was already observed
+        ptx::tc_fence_after();
+        const uint64_t dq = ptx::make_sw128_desc(ptx::smem_u32(sQ + g * TILE_BYTES));
+        const uint64_t dk = ptx::make_sw128_desc(ptx::smem_u32(sKV + st * 2 * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::umma_bf16(tmem_base + g * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        ptx::umma_commit(&s_full[g]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(item, npairs, a.H, N);
+        const int ng = it.has_b ? 2 : 1;
+        for (int g = 0; g < ng; ++g) {
+          ptx::mbar_wait(&q_full[g], items_g[g] & 1);
+          issue_s(g, gt0);
+          if (n_kv == 1) ptx::umma_commit(&q_empty[g]);
+        }
+        int done[2] = {0, ng == 2 ? 0 : n_kv};
+        while (done[0] < n_kv || done[1] < n_kv) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (done[g] >= n_kv) continue;
+            if (!ptx::mbar_try_wait(&p_full[g], tiles_g[g] & 1)) continue;  // P_g(t) stored, S_g(t) read out of TMEM
+            const int t = done[g];
+            if (t + 1 < n_kv) {
+              // never block here: the stage of tile t+1 may only free up after the OTHER group's PV, issued by this thread
+              const uint32_t gn = gt0 + t + 1;
+              if (!ptx::mbar_try_wait(&kv_full[gn % KV_STAGES], (gn / KV_STAGES) & 1)) continue;
+            }
+            ptx::tc_fence_after();
+            if (t + 1 < n_kv) {
+              issue_s(g, gt0 + t + 1);
+              if (t + 2 == n_kv) ptx::umma_commit(&q_empty[g]);  // last S of the item: Q_g may be overwritten
+            }
+            if (t == 0) {
+              ptx::mbar_wait(&o_free[g], (items_g[g] & 1) ^ 1);  // previous item's O_g has been drained
+              ptx::tc_fence_after();
+            }
+            const int st = (gt0 + t) % KV_STAGES;
+            const uint64_t dp = ptx::make_sw128_desc(ptx::smem_u32(sP + g * 2 * TILE_BYTES));
+            const uint64_t dv = ptx::make_sw128_desc(ptx::smem_u32(sKV + st * 2 * TILE_BYTES + TILE_BYTES));
+#pragma unroll
+            for (int ks = 0; ks < BKV / 16; ++ks) {
+              // A: P, K-major, two 64-key swizzle atoms 16 KB apart; B: V rows = keys (MN-major), 16 keys = 2048 bytes
+              const uint64_t da = dp + (uint64_t)((ks >> 2) * (TILE_BYTES >> 4) + 2 * (ks & 3));
+              const uint64_t db = dv + (uint64_t)(ks * (2048 >> 4));
+              ptx::umma_bf16(tmem_base + 256 + g * 64, da, db, idesc_o, (t | ks) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&o_full[g]);
+            ++done[g];
+            ++tiles_g[g];
+            // the stage of tile t is free once both groups' MMAs on it retire; the group that issues last commits
+            if (ng == 1 || done[g ^ 1] > t) ptx::umma_commit(&kv_empty[st]);
+          }
+        }
+        gt0 += n_kv;
+        for (int g = 0; g < ng; ++g) ++items_g[g];
+      }
+    }
+  } else {
+    // ===================== softmax groups =====================
+    const int g = warp >> 3;
+    const int quarter = warp & 3, ch = (warp >> 2) & 1;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const int stid = tid & (GROUP_THREADS - 1);
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * 128, tmem_o = tmem_base + 256 + g * 64;
+    const uint32_t tab_a = smem_a + OFF_TAB + g * TAB_BYTES;
+    const uint32_t win_a = tab_a + TAB_WIN, mask_a = tab_a + TAB_MASK, pmax_a = tab_a + TAB_PMAX;
+    const uint32_t q_a = smem_a + OFF_Q + g * TILE_BYTES + r * 128;
+    const uint32_t p_a = smem_a + OFF_P + g * 2 * TILE_BYTES + ch * TILE_BYTES + r * 128;
+    const bool has_pad = a.key_pad != nullptr;
+    const float qk_scale = 0.125f * LOG2E;  // head_dim^-0.5 (backbone.py:403), exp2 domain
+    const int shift = (r + 1) & 3;          // which shifted window copy makes (c - r + 127 + shift) a multiple of 4
+    const uint32_t win_row = win_a + (win_copy_offset(shift) + ch * 64 - r + 127 + shift) * 4;
+    const int bar_id = 1 + g;
+    const uint64_t* sfull = &s_full[g];
+    const uint64_t* ofull = &o_full[g];
+    uint32_t items = 0, tiles = 0;
+
+    // table entries of a tile: thread stid < 255 owns entry stid of the bias window, thread stid < 128 one mask entry
+    auto fetch_bias = [&](const Item& it, int t) -> float {
+      const int q0 = it.q0 + g * BQ;
+      const int rel = t * BKV - q0 - 127 + stid;  // j - i
+      return (stid < 255 && rel > -N && rel < N) ? __ldg(a.bias_vec + (size_t)it.h * (2 * N - 1) + (N - 1) + rel) * LOG2E : 0.f;
+    };
+    auto fetch_dead = [&](const Item& it, int t) -> bool {
+      const int j = t * BKV + stid;
+      bool dead = j >= N;
+      if (stid < BKV && !dead && has_pad) dead = a.key_pad[(size_t)it.b * N + j] != 0;
+      return dead;
+    };
+    auto store_tables = [&](int t, float bv, bool dead) {
+      const uint32_t wbuf = win_a + (t & 1) * WIN_FLOATS * 4;
+      if (stid < 255) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) sts32(wbuf + (win_copy_offset(s) + stid + s) * 4, bv);
+      }
+      if (stid < BKV) sts32(mask_a + ((t & 1) * BKV + stid) * 4, dead ? -INFINITY : 0.f);
+    };
+    // tile-0 entries of the next item are fetched during the last tile of the current one (pref_*)
+    bool have_pref = false;
+    float pref_bias = 0.f, pref_grep = 0.f;
+    bool pref_dead = false;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode_item(item, npairs, a.H, N);
+      if (g == 1 && !it.has_b) continue;
+      const int q0 = it.q0 + g * BQ, b = it.b, h = it.h;
+      const uint8_t* kpad = has_pad ? a.key_pad + (size_t)b * N : nullptr;
+      if (!have_pref) {
+        pref_bias = fetch_bias(it, 0);
+        pref_dead = fetch_dead(it, 0);
+        pref_grep = __ldg(a.grep_a + h);
+      }
+      const float grep_a = pref_grep;
+      store_tables(0, pref_bias, pref_dead);
+      have_pref = false;
+      Item nit = it;
+      bool next_ok = false;
+      if (item + (int)gridDim.x < n_items) {
+        nit = decode_item(item + gridDim.x, npairs, a.H, N);
+        next_ok = !(g == 1 && !nit.has_b);
+      }
+
+      // first tile that holds a valid key (0 unless the clip starts with >= 128 padded keys): group-uniform
+      int t_first = 0;
+      if (has_pad) {
+        int jmin = N;
+        for (int j = stid; j < N; j += GROUP_THREADS)
+          if (kpad[j] == 0) { jmin = j; break; }
+        if (stid == 0) sts32(pmax_a + 1024 * 4, __int_as_float(N));
+        named_bar_sync(bar_id, GROUP_THREADS);
+        if (jmin < N) atomicMin(reinterpret_cast<int*>(smem + OFF_TAB + g * TAB_BYTES + TAB_PMAX) + 1024, jmin);
+        named_bar_sync(bar_id, GROUP_THREADS);
+        t_first = __float_as_int(lds32(pmax_a + 1024 * 4)) / BKV;  // == n_kv when every key is padded: pass A never runs
+      }
+
+      // gate per query row from UNscaled q (backbone.py:544-550): thread ch computes sigmoid half ch, partners swap
+      ptx::mbar_wait(&q_full[g], items & 1);
+      float sg;
+      {
+        float acc0 = 0.f, acc1 = 0.f;
+        const uint32_t gw_a = smem_a + OFF_GATEW + ch * 256;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 raw = lds128u(q_a + ((c ^ (r & 7)) << 4));
+          const float4 w0 = lds128(gw_a + c * 32), w1 = lds128(gw_a + c * 32 + 16);
+          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          const float2 f0 = __bfloat1622float2(p2[0]), f1 = __bfloat1622float2(p2[1]);
+          const float2 f2 = __bfloat1622float2(p2[2]), f3 = __bfloat1622float2(p2[3]);
+          acc0 = fmaf(f0.x, w0.x, acc0); acc1 = fmaf(f0.y, w0.y, acc1);
+          acc0 = fmaf(f1.x, w0.z, acc0); acc1 = fmaf(f1.y, w0.w, acc1);
+          acc0 = fmaf(f2.x, w1.x, acc0); acc1 = fmaf(f2.y, w1.y, acc1);
+          acc0 = fmaf(f3.x, w1.z, acc0); acc1 = fmaf(f3.y, w1.w, acc1);
+        }
+        const float z = acc0 + acc1 + lds32(smem_a + OFF_GATEW + 512 + ch * 4);
+        sg = 1.0f / (1.0f + __expf(-z));
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&q_empty[g]);
+      sts32(pmax_a + (768 + ch * 128 + r) * 4, sg);
+      named_bar_sync(bar_id, GROUP_THREADS);  // tables of tile 0 and the sigmoid halves are visible
+      float gate;
+      {
+        const float other = lds32(pmax_a + (768 + (ch ^ 1) * 128 + r) * 4);
+        const float ga = ch == 0 ? sg : other, gb = ch == 0 ? other : sg;
+        gate = ga * (gb * grep_a - 1.0f) + 2.0f;  // gate_a*(gate_b*grep_a-1)+2
+      }
+
+      // m_run: reference max of the row (log2 domain).  Exact after pass A on tile t_first; afterwards it only moves
+      // (between tiles) when a tile's max exceeds it by more than RESCALE_THRESHOLD -- O and l are rescaled by
+      // `pending` at the start of the next tile.  The result is exact after the final 1/l for any reference.
+      float m_run = -INFINITY, l_run = 0.f, pending = 1.0f;
+      for (int t = 0; t < n_kv; ++t) {
+        const bool masked = has_pad || (N - t * BKV < BKV);
+        const bool more = t + 1 < n_kv;
+        float nbias = 0.f;
+        bool ndead = false;
+        if (more) {  // global loads in flight during the tile
+          nbias = fetch_bias(it, t + 1);
+          ndead = fetch_dead(it, t + 1);
+        } else if (next_ok) {
+          pref_bias = fetch_bias(nit, 0);
+          pref_dead = fetch_dead(nit, 0);
+          pref_grep = __ldg(a.grep_a + nit.h);
+          have_pref = true;
+        }
+        const uint32_t taddr = tmem_s + lane_addr + ch * 64;
+        const uint32_t wrow = win_row + (t & 1) * WIN_FLOATS * 4;
+        const uint32_t mrow = mask_a + ((t & 1) * BKV + ch * 64) * 4;
+        ptx::mbar_wait(const_cast<uint64_t*>(sfull), tiles & 1);
+        ptx::tc_fence_after();
+        if (t == t_first) {
+          const float pm = masked ? score_max<true>(taddr, wrow, mrow, gate, qk_scale)
+                                  : score_max<false>(taddr, wrow, mrow, gate, qk_scale);
+          sts32(pmax_a + (512 + ch * 128 + r) * 4, pm);
+          named_bar_sync(bar_id, GROUP_THREADS);
+          m_run = fmaxf(pm, lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4));  // finite: the tile has a valid key
+        }
+        if (t > 0) {
+          ptx::mbar_wait(const_cast<uint64_t*>(ofull), (tiles - 1) & 1);  // PV(t-1) retired: O consistent, P buffer free
+          ptx::tc_fence_after();
+          if (__any_sync(0xffffffffu, pending != 1.0f)) {
+            l_run *= pending;
+#pragma unroll 1
+            for (int hc = 0; hc < 2; ++hc) {
+              uint32_t o[16];
+              const uint32_t oaddr = tmem_o + lane_addr + ch * 32 + hc * 16;
+              tmem_ld_32x16(oaddr, o);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * pending);
+              tmem_st_32x16(oaddr, o);
+            }
+            tmem_st_wait();
+          }
+        }
+        const float m_eff = m_run == -INFINITY ? 0.f : m_run;  // -inf only while every key so far was masked (p = 0)
+        float mx, sum;
+        if (masked) stream_tile<true>(taddr, wrow, mrow, gate, qk_scale, m_eff, p_a, r & 7, mx, sum);
+        else stream_tile<false>(taddr, wrow, mrow, gate, qk_scale, m_eff, p_a, r & 7, mx, sum);
+        l_run += sum;
+        ptx::fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async proxy
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[g]);
+        ++tiles;
+        // off the critical path: join the tile max with the partner, decide the reference for the next tile
+        pending = 1.0f;
+        if (more) {
+          sts32(pmax_a + (((t & 1) * 2 + ch) * 128 + r) * 4, mx);
+          store_tables(t + 1, nbias, ndead);
+          named_bar_sync(bar_id, GROUP_THREADS);
+          const float m_tile = fmaxf(mx, lds32(pmax_a + (((t & 1) * 2 + (ch ^ 1)) * 128 + r) * 4));
+          if (m_run != -INFINITY && m_tile > m_run + RESCALE_THRESHOLD) {
+            pending = ex2(m_run - m_tile);
+            m_run = m_tile;
+          }
+        }
+      }
+
+      // ---- finalise: O / l -> bf16 -------------------------------------------------------------------------------
+      named_bar_sync(bar_id, GROUP_THREADS);  // pass-A exchange slots are free again
+      sts32(pmax_a + (512 + ch * 128 + r) * 4, l_run);
+      named_bar_sync(bar_id, GROUP_THREADS);
+      const float l_tot = l_run + lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4);
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      ptx::mbar_wait(const_cast<uint64_t*>(ofull), (tiles - 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(tmem_o + lane_addr + ch * 32, o);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&o_free[g]);  // O_g is in registers: the next item's first PV may overwrite it
+      if (q0 + r < N) {
+        __nv_bfloat16* dst = a.out + ((size_t)b * N + q0 + r) * (size_t)(a.H * HD) + h * HD + ch * 32;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 pk;
+          pk.x = pack_bf16(__uint_as_float(o[8 * c + 0]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          pk.y = pack_bf16(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          pk.z = pack_bf16(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          pk.w = pack_bf16(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 8) = pk;
+        }
+      }
+      ++items;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+}  // namespace avexk
+
+extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const float* gate_w, const float* gate_b,
+                                     const float* grep_a, const float* bias_vec, const uint8_t* key_pad, void* out,
+                                     void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(qkv && gate_w && gate_b && grep_a && bias_vec && out, "avexk_attention_gated: null argument");
+  AVEXK_CHECK_ARG(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "avexk_attention_gated: bad shape B=%d N=%d H=%d", B, N, H);
+  AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  "avexk_attention_gated: qkv/out must be 16-byte aligned");
+  if (B == 0) return AVEXK_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVEXK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  // qkv viewed as [B][N][3*H*64]: rows past the end of a clip are out of bounds -> zero-filled by TMA
+  CUtensorMap map;
+  const long long C3 = 3LL * H * HD;
+  int rc = make_tmap_3d_bf16(&map, qkv, C3, N, B, C3, (long long)N * C3, HD, BQ, 1, true);
+  if (rc) return rc;
+  AttnTcArgs a{B, N, H, gate_w, gate_b, grep_a, bias_vec, key_pad, reinterpret_cast<__nv_bfloat16*>(out)};
+  const long long items = (long long)B * H * ceil_div(N, 2 * BQ);
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  prof_begin(st, KID_ATTN, 4.0 * B * H * (double)N * N * HD);
+  attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, a);
+  prof_end(st);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}

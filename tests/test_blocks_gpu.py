@@ -111,7 +111,8 @@ def _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, key_pad):
     return (p @ v).permute(0, 2, 1, 3).reshape(B * N, H * d)
 
 
-@pytest.mark.parametrize("B,N,H,pad", [(2, 48, 12, False), (1, 248, 12, False), (3, 96, 4, True), (2, 496, 2, False), (1, 700, 1, True)])
+@pytest.mark.parametrize("B,N,H,pad", [(2, 48, 12, False), (1, 248, 12, False), (3, 96, 4, True), (2, 496, 2, False), (1, 700, 1, True),
+                                         (1, 128, 1, False), (2, 256, 3, False), (1, 2992, 2, False), (40, 496, 12, False), (2, 300, 2, True)])
 def test_attention_gated(lib, B, N, H, pad):
     g = torch.Generator(device="cuda").manual_seed(N)
     qkv = (torch.randn(B * N, 3 * H * 64, device="cuda", generator=g)).to(torch.bfloat16)
@@ -131,6 +132,52 @@ def test_attention_gated(lib, B, N, H, pad):
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all()
     assert err <= 2e-2, err  # P and the output are rounded to bf16
+    assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
+
+
+def test_attention_leading_padding(lib):
+    """Keys 0..139 of clip 0 are padded: the first 128-key tile is fully masked (exercises the deferred exact-max pass)."""
+    B, N, H = 2, 300, 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = (torch.randn(B * N, 3 * H * 64, device="cuda", generator=g) * 2.0).to(torch.bfloat16)
+    gw = torch.randn(2, 64, device="cuda", generator=g) * 0.2
+    gb = torch.randn(2, device="cuda", generator=g) * 0.2
+    ga = 1.0 + 0.2 * torch.randn(H, device="cuda", generator=g)
+    table = torch.randn(320, H, generator=torch.Generator().manual_seed(2)) * 3.0
+    bias_vec = torch.from_numpy(OR.bias_vector(table.numpy(), N)).cuda()
+    key_pad = torch.zeros(B, N, dtype=torch.uint8, device="cuda")
+    key_pad[0, :140] = 1
+    key_pad[1, 200:] = 1
+    out = torch.empty(B * N, H * 64, device="cuda", dtype=torch.bfloat16)
+    _check(lib.avexk_attention_gated(qkv.data_ptr(), B, N, H, gw.data_ptr(), gb.data_ptr(), ga.data_ptr(), bias_vec.data_ptr(),
+                                     key_pad.data_ptr(), out.data_ptr(), _stream()), lib)  # fmt: skip
+    ref = _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, key_pad)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-2, err  # |v| ~ 2, sharp softmax
+    assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
+
+
+def test_attention_large_score_growth(lib):
+    """Scores that grow along the key axis force the lazy reference max to move on every tile (rescale path)."""
+    B, N, H = 1, 640, 2
+    g = torch.Generator(device="cuda").manual_seed(9)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g)
+    ramp = torch.linspace(0.2, 6.0, N, device="cuda")[:, None]
+    qkv[:, H * 64 : 2 * H * 64] *= ramp  # keys get larger with j
+    qkv = qkv.to(torch.bfloat16)
+    gw = torch.randn(2, 64, device="cuda", generator=g) * 0.2
+    gb = torch.randn(2, device="cuda", generator=g) * 0.2
+    ga = 1.0 + 0.2 * torch.randn(H, device="cuda", generator=g)
+    table = torch.randn(320, H, generator=torch.Generator().manual_seed(3))
+    bias_vec = torch.from_numpy(OR.bias_vector(table.numpy(), N)).cuda()
+    out = torch.empty(B * N, H * 64, device="cuda", dtype=torch.bfloat16)
+    _check(lib.avexk_attention_gated(qkv.data_ptr(), B, N, H, gw.data_ptr(), gb.data_ptr(), ga.data_ptr(), bias_vec.data_ptr(),
+                                     None, out.data_ptr(), _stream()), lib)  # fmt: skip
+    ref = _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, None)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 3e-2, err
     assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
 
 
