@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS, not generic LD/ST)
   unsigned char* stage_base = smem;
   float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);

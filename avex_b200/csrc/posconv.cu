@@ -2,13 +2,17 @@
 //
 // Replaces avex/models/beats/backbone.py:52-68,172-174 + modules.py:67-94:
 //   y = x + GELU(Conv1d(C, C, k=128, pad=64, groups=16)(x^T)[:, :, :N]^T)      (weight-norm resolved at load)
-// as 16 implicit GEMMs, one per channel group: for a tile of 128 tokens of one clip and group g
+// as 16 implicit GEMMs, one per channel group.  For a super-tile of 256 tokens of one clip and group g
 //   acc[n, co] = sum_{t<128} sum_{ci<48} x[n + t - 64, g*48 + ci] * w[g*48 + co, ci, t]
-// Tap t is one K-block: the A operand is the SAME activation tile shifted by t rows, fetched by TMA from the
-// group-padded bf16 copy xg [B, N, 16*64] through a 3-D tensor map whose out-of-bounds rows (n < 0, n >= N)
-// are zero-filled by hardware -- exactly the conv's zero padding, per clip.  B operand = packed weights
-// Wpc [C, 128*64] (K index = t*64 + ci).  UMMA shape 128 x 48 x 16, accumulators in TMEM (2 x 64 columns).
+// The activation window (rows n0-64 .. n0+319 of the group-padded bf16 copy xg [B, N, 16*64]) is loaded ONCE per
+// super-tile by TMA (3-D tensor map: rows outside the clip are zero-filled by hardware -- exactly the conv's zero
+// padding).  Tap t is one K-block whose A operand is that same window shifted down by t rows: the UMMA shared-memory
+// descriptor simply starts t*128 bytes later (the hardware swizzles on absolute address bits, so the phase still matches
+// what TMA wrote).  Only the per-tap weight tile (48 x 48, 6 KB) streams through the TMA ring, and it
+// is shared by the two 128-token halves of the super-tile.  UMMA shape 128 x 48 x 16, K = 48 per tap (the 16 pad
+// channels are never multiplied); accumulators in TMEM (2 buffers x 2 halves x 64 columns).
 // Epilogue: + bias, GELU, + x0 (residual), fp32 store.
+// Roofline: shared-memory operand bandwidth (A 12 KB + W 4.5 KB per tap per half at 128 B/clk), then the tensor pipe.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -17,9 +21,11 @@
 namespace avexk {
 namespace {
 
-constexpr int BM = 128, CG = 48, BK = 64, TAPS = 128, STAGES = 8;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = CG * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // 16384 + 6144
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+constexpr int BM = 128, HALVES = 2, SUPER = BM * HALVES, CG = 48, TAPS = 128, WSTAGES = 8;
+constexpr int WIN_BOXES = 3, WIN_ROWS = WIN_BOXES * 128;       // rows n0-64 .. n0+319 (383 needed)
+constexpr int WIN_BYTES = WIN_ROWS * 128, W_BYTES = CG * 128;  // 49152, 6144 (both multiples of 1024)
+constexpr int OFF_W = 2 * WIN_BYTES, OFF_BAR = OFF_W + WSTAGES * W_BYTES;
+constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
 constexpr int NTHREADS = 192;
 constexpr int ACC_COLS = 64;
 
@@ -39,16 +45,26 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+// K-major SWIZZLE_128B operand that starts `row` 128-byte rows below a 1024-byte aligned base.  The tensor core applies
+// the 128-byte swizzle to ABSOLUTE shared-memory address bits (as TMA does when it writes the tile), so a start address
+// that is only 128-byte aligned reads the shifted rows correctly with the descriptor's base-offset field left at 0
+// (measured on B200: base_offset = row mod 8 gives wrong data, 0 is bit-correct against the oracle).
+__device__ __forceinline__ uint64_t make_sw128_desc_rows(uint32_t base_addr, int row) {
+  return ptx::make_sw128_desc(base_addr + row * 128);
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 posconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const PcArgs g) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* win_full = bars;                  // [2]
+  uint64_t* win_empty = bars + 2;             // [2]
+  uint64_t* w_full = bars + 4;                // [WSTAGES]
+  uint64_t* w_empty = bars + 4 + WSTAGES;     // [WSTAGES]
+  uint64_t* tfull_bar = bars + 4 + 2 * WSTAGES;   // [2]
+  uint64_t* tempty_bar = bars + 6 + 2 * WSTAGES;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * WSTAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = g.G * CG;
@@ -57,18 +73,20 @@ posconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_x);
     ptx::prefetch_tensormap(&map_w);
-    for (int i = 0; i < STAGES; ++i) {
-      ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
-    }
     for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&win_full[i], 1);
+      ptx::mbar_init(&win_empty[i], 1);
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], 4);
+    }
+    for (int i = 0; i < WSTAGES; ++i) {
+      ptx::mbar_init(&w_full[i], 1);
+      ptx::mbar_init(&w_empty[i], 1);
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 2 * ACC_COLS);
+    ptx::tmem_alloc(tmem_slot, 2 * HALVES * ACC_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -76,86 +94,100 @@ posconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (clip b, token tile nt, group grp); groups fastest so concurrent CTAs share the activation rows in L2
+  // tile -> (clip b, super-tile nt, group grp); groups fastest so concurrent CTAs share the activation rows in L2
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      auto load_window = [&](int tile, int it) {
         const int grp = tile % g.G, mt = tile / g.G;
         const int nt = mt % g.tiles_per_clip, b = mt / g.tiles_per_clip;
+        const int wb = it & 1;
+        ptx::mbar_wait(&win_empty[wb], ((it >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&win_full[wb], WIN_BYTES);
+        for (int bx = 0; bx < WIN_BOXES; ++bx)
+          ptx::tma_load_3d(smem + wb * WIN_BYTES + bx * 128 * 128, &map_x, &win_full[wb], grp * 64,
+                           nt * SUPER - TAPS / 2 + bx * 128, b);
+      };
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      if (blockIdx.x < num_tiles) load_window(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        if (tile + (int)gridDim.x < num_tiles) load_window(tile + gridDim.x, it + 1);  // one super-tile ahead
+        const int grp = tile % g.G;
         for (int t = 0; t < TAPS; ++t) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          unsigned char* sa = smem + stage * STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          ptx::tma_load_3d(sa, &map_x, &full_bar[stage], grp * 64, nt * BM + t - TAPS / 2, b);  // rows n + t - 64
-          ptx::tma_load_2d(sa + A_BYTES, &map_w, &full_bar[stage], t * BK, grp * CG);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::mbar_wait(&w_empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&w_full[stage], W_BYTES);
+          ptx::tma_load_2d(smem + OFF_W + stage * W_BYTES, &map_w, &w_full[stage], t * 64, grp * CG);
+          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, CG);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      for (int t = 0; t < TAPS; ++t) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, CG);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1, wb = it & 1;
+        ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&win_full[wb], (it >> 1) & 1);
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sa + A_BYTES);
+        const uint32_t win_addr = ptx::smem_u32(smem + wb * WIN_BYTES);
+        for (int t = 0; t < TAPS; ++t) {
+          ptx::mbar_wait(&w_full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t db = ptx::make_sw128_desc(ptx::smem_u32(smem + OFF_W + stage * W_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
-          ptx::umma_commit(&empty_bar[stage]);
-          if (t == TAPS - 1) ptx::umma_commit(&tfull_bar[acc]);
+          for (int hf = 0; hf < HALVES; ++hf) {
+            const uint64_t da = make_sw128_desc_rows(win_addr, hf * BM + t);
+            const uint32_t d_tmem = tmem_base + (acc * HALVES + hf) * ACC_COLS;
+#pragma unroll
+            for (int k = 0; k < CG / 16; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&w_empty[stage]);
+          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        ptx::umma_commit(&tfull_bar[acc]);
+        ptx::umma_commit(&win_empty[wb]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int quarter = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
       const int grp = tile % g.G, mt = tile / g.G;
       const int nt = mt % g.tiles_per_clip, b = mt / g.tiles_per_clip;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * ACC_COLS;
-      const int n = nt * BM + quarter * 32 + lane;  // token inside the clip (one row per lane)
-      const size_t row_off = ((size_t)b * g.N + n) * C + grp * CG;
+#pragma unroll 1
+      for (int hf = 0; hf < HALVES; ++hf) {
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * HALVES + hf) * ACC_COLS;
+        const int n = nt * SUPER + hf * BM + quarter * 32 + lane;  // token inside the clip (one row per lane)
+        const size_t row_off = ((size_t)b * g.N + n) * C + grp * CG;
 #pragma unroll
-      for (int c = 0; c < CG / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld_32x16(t_addr + c * 16, r);
-        ptx::tmem_ld_wait();
-        if (n < g.N) {
+        for (int c = 0; c < CG / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld_32x16(t_addr + c * 16, r);
+          ptx::tmem_ld_wait();
+          if (n < g.N) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int col = c * 16 + i * 4;
-            const float4 bs = __ldg(reinterpret_cast<const float4*>(g.bias + grp * CG + col));
-            const float4 rs = __ldg(reinterpret_cast<const float4*>(g.x0 + row_off + col));
-            float4 v;
-            v.x = gelu_erf(__uint_as_float(r[4 * i + 0]) + bs.x) + rs.x;
-            v.y = gelu_erf(__uint_as_float(r[4 * i + 1]) + bs.y) + rs.y;
-            v.z = gelu_erf(__uint_as_float(r[4 * i + 2]) + bs.z) + rs.z;
-            v.w = gelu_erf(__uint_as_float(r[4 * i + 3]) + bs.w) + rs.w;
-            *reinterpret_cast<float4*>(g.out + row_off + col) = v;
+            for (int i = 0; i < 4; ++i) {
+              const int col = c * 16 + i * 4;
+              const float4 bs = __ldg(reinterpret_cast<const float4*>(g.bias + grp * CG + col));
+              const float4 rs = __ldg(reinterpret_cast<const float4*>(g.x0 + row_off + col));
+              float4 v;
+              v.x = gelu_erf(__uint_as_float(r[4 * i + 0]) + bs.x) + rs.x;
+              v.y = gelu_erf(__uint_as_float(r[4 * i + 1]) + bs.y) + rs.y;
+              v.z = gelu_erf(__uint_as_float(r[4 * i + 2]) + bs.z) + rs.z;
+              v.w = gelu_erf(__uint_as_float(r[4 * i + 3]) + bs.w) + rs.w;
+              *reinterpret_cast<float4*>(g.out + row_off + col) = v;
+            }
           }
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -163,7 +195,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    ptx::tmem_dealloc(tmem_base, 2 * HALVES * ACC_COLS);
   }
 }
 
@@ -180,11 +212,11 @@ int launch_posconv(const __nv_bfloat16* xg, const __nv_bfloat16* Wpc, const floa
     attr_set = true;
   }
   CUtensorMap mx, mw;
-  int rc = make_tmap_3d_bf16(&mx, xg, (long long)G * 64, N, B, (long long)G * 64, (long long)N * G * 64, 64, BM, 1, true);
+  int rc = make_tmap_3d_bf16(&mx, xg, (long long)G * 64, N, B, (long long)G * 64, (long long)N * G * 64, 64, 128, 1, true);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&mw, Wpc, (long long)G * CG, (long long)TAPS * 64, (long long)TAPS * 64, CG, BK);
+  rc = make_tmap_2d_bf16(&mw, Wpc, (long long)G * CG, (long long)TAPS * 64, (long long)TAPS * 64, CG, 64);
   if (rc) return rc;
-  PcArgs a{B, N, G, ceil_div(N, BM), bias, x0, out};
+  PcArgs a{B, N, G, ceil_div(N, SUPER), bias, x0, out};
   const int tiles = B * a.tiles_per_clip * G;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_begin(st, KID_POSCONV, 2.0 * B * N * (double)(G * CG) * CG * TAPS);
