@@ -78,6 +78,49 @@ SIGNATURES = {
     "avexk_beats_forward": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp, _vp, _sz, _vp]),
 }
 
+
+
+class EffnetBlockCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("kernel", "stride", "cin", "cexp", "cout", "csq")]
+
+
+class BnParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("weight", "bias", "mean", "var")]
+
+
+class EffnetBlockWeights(C.Structure):
+    _fields_ = [
+        ("expand_w", C.c_void_p), ("expand_bn", BnParams),
+        ("dw_w", C.c_void_p), ("dw_bn", BnParams),
+        ("se1_w", C.c_void_p), ("se1_b", C.c_void_p), ("se2_w", C.c_void_p), ("se2_b", C.c_void_p),
+        ("proj_w", C.c_void_p), ("proj_bn", BnParams),
+    ]  # fmt: skip
+
+
+class EffnetWeights(C.Structure):
+    _fields_ = [
+        ("stem_w", C.c_void_p), ("stem_bn", BnParams),
+        ("blocks", C.POINTER(EffnetBlockWeights)),
+        ("head_w", C.c_void_p), ("head_bn", BnParams),
+        ("cls_w", C.c_void_p), ("cls_b", C.c_void_p), ("num_classes", C.c_int),
+    ]  # fmt: skip
+
+
+SIGNATURES.update({
+    "avexk_melspec_create": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "avexk_melspec_destroy": (None, [_vp]),
+    "avexk_melspec_num_frames": (_i, [_i]),
+    "avexk_melspec_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
+    "avexk_conv1x1_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "avexk_dwconv_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "avexk_effnet_create": (_i, [C.POINTER(EffnetBlockCfg), _i, _i, _i, C.POINTER(_vp)]),
+    "avexk_effnet_destroy": (None, [_vp]),
+    "avexk_effnet_load_weights": (_i, [_vp, C.POINTER(EffnetWeights), _vp]),
+    "avexk_effnet_out_hw": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "avexk_effnet_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "avexk_effnet_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, C.POINTER(_vp), _vp, _sz, _vp]),
+})
+
 _lib = None
 
 

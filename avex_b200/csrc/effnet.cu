@@ -1,0 +1,587 @@
+// effnet.cu -- EfficientNet-B0/B1 feature extractor forward (torchvision topology) as NHWC bf16 kernels.
+//
+// Replaces `efficientnet.Model.forward` (avex/models/efficientnet.py:163-215): the 3-channel repeat of the mel image
+// (efficientnet.py:138-140), torchvision `efficientnet_b0().features` (stem conv, 16 MBConv blocks, head conv; BatchNorm
+// in eval mode, SiLU, squeeze-excitation), `avgpool` and the classifier.
+//   * the 3 identical input channels are never materialised: the stem kernel uses the conv weights summed over C_in and
+//     applies the per-clip min-max normalisation of the mel image (audio_utils.py:167-172) on load;
+//   * activations live in HBM as NHWC bf16, so every 1x1 convolution (88 % of the MACs) is a plain GEMM
+//     [B*H*W, C_in] x [C_out, C_in]^T on the tcgen05 kernel of gemm_tc.cu with the folded BatchNorm, SiLU and the
+//     residual add in its epilogue; the raw (pre-BN) conv output that a forward hook on `block.3.0` / `features.8.0`
+//     sees is stored from the same epilogue when requested;
+//   * depthwise k x k convolutions are memory-bound stencils: one thread = 8 channels (one 16-byte vector) of one output
+//     pixel, BN + SiLU fused, and the squeeze-excitation global average accumulated on the way out (registers ->
+//     shared-memory atomics -> one global atomic per (CTA, channel));
+//   * SE: a tiny per-clip MLP kernel, then the channel scale applied in place.
+// Roofline: HBM (about 29 FLOP/B overall); the pointwise GEMMs are reported against the tensor pipe.
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+struct avexk_effnet {
+  std::vector<avexk_effnet_block_cfg> cfg;
+  bool loaded = false;
+  int num_classes = 0;
+  std::vector<void*> allocs;
+  // stem
+  float *stem_w = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;  // [9][32], [32], [32]
+  struct Block {
+    __nv_bfloat16 *expand_w = nullptr, *proj_w = nullptr;
+    float *expand_scale = nullptr, *expand_shift = nullptr, *dw_w = nullptr, *dw_scale = nullptr, *dw_shift = nullptr;
+    float *se1_w = nullptr, *se1_b = nullptr, *se2_w = nullptr, *se2_b = nullptr, *proj_scale = nullptr, *proj_shift = nullptr;
+  };
+  std::vector<Block> blocks;
+  __nv_bfloat16* head_w = nullptr;
+  float *head_scale = nullptr, *head_shift = nullptr, *cls_w = nullptr, *cls_b = nullptr;
+  int stem_out = 32, head_in = 320, head_out = 1280;
+};
+
+namespace avexk {
+namespace {
+
+__device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float dec_ordered(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// BatchNorm (eval) -> per-channel scale / shift: y = x * scale + shift, eps 1e-5 (torchvision default)
+__global__ void bn_fold_kernel(const float* w, const float* b, const float* mean, const float* var, float eps, int C,
+                               float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float s = w[c] / sqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = b[c] - mean[c] * s;
+  }
+}
+
+// stem weights [32, 3, 3, 3] -> [9][32] summed over the three identical input channels
+__global__ void stem_pack_kernel(const float* w, int Cout, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // tap * Cout + co
+  if (i < 9 * Cout) {
+    const int co = i % Cout, tap = i / Cout;
+    out[i] = w[(co * 3 + 0) * 9 + tap] + w[(co * 3 + 1) * 9 + tap] + w[(co * 3 + 2) * 9 + tap];
+  }
+}
+
+// depthwise weights [C, 1, k, k] -> [k*k][C]
+__global__ void dw_pack_kernel(const float* w, int C, int kk, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * kk) {
+    const int c = i % C, tap = i / C;
+    out[i] = w[c * kk + tap];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stem: 3x3 stride-2 pad-1 conv on the (normalised-on-load) mel image [B, 128, Tm] -> NHWC bf16 [B, Ho, Wo, 32]
+// ---------------------------------------------------------------------------------------------------------
+constexpr int STEM_C = 32;
+__global__ void __launch_bounds__(256)
+stem_kernel(const float* __restrict__ mel, const unsigned* __restrict__ minmax, int B, int H, int W, int Ho, int Wo,
+            const float* __restrict__ w9, const float* __restrict__ scale, const float* __restrict__ shift,
+            __nv_bfloat16* __restrict__ out, float* __restrict__ raw_nchw) {
+  __shared__ float sw[9 * STEM_C], ss[STEM_C], sh[STEM_C];
+  for (int i = threadIdx.x; i < 9 * STEM_C; i += blockDim.x) sw[i] = w9[i];
+  if (threadIdx.x < STEM_C) {
+    ss[threadIdx.x] = scale[threadIdx.x];
+    sh[threadIdx.x] = shift[threadIdx.x];
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Ho * Wo) return;
+  const int ho = p / Wo, wo = p - ho * Wo;
+  float mn = 0.f, inv = 1.f;
+  if (minmax != nullptr) {
+    mn = dec_ordered(minmax[2 * b]);
+    inv = 1.0f / (dec_ordered(minmax[2 * b + 1]) - mn + 1e-8f);
+  }
+  const float* img = mel + (size_t)b * H * W;
+  float v[9];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int hi = 2 * ho - 1 + ky, wi = 2 * wo - 1 + kx;
+      const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+      v[ky * 3 + kx] = ok ? (__ldg(img + (size_t)hi * W + wi) - mn) * inv : 0.f;  // zero padding of the normalised image
+    }
+  uint32_t packed[STEM_C / 2];
+#pragma unroll
+  for (int c = 0; c < STEM_C; c += 2) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      a0 = fmaf(v[t], sw[t * STEM_C + c], a0);
+      a1 = fmaf(v[t], sw[t * STEM_C + c + 1], a1);
+    }
+    if (raw_nchw != nullptr) {
+      raw_nchw[((size_t)b * STEM_C + c) * Ho * Wo + p] = a0;
+      raw_nchw[((size_t)b * STEM_C + c + 1) * Ho * Wo + p] = a1;
+    }
+    packed[c / 2] = pack_bf16(silu(fmaf(a0, ss[c], sh[c])), silu(fmaf(a1, ss[c + 1], sh[c + 1])));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * Ho * Wo + p) * STEM_C);
+#pragma unroll
+  for (int i = 0; i < STEM_C / 8; ++i) dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// depthwise k x k conv + BN + SiLU, NHWC bf16, with the squeeze-excitation sums
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DW_PIX = 256;  // output pixels per CTA
+template <int K>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho, int Wo, int stride,
+              const float* __restrict__ wkk, const float* __restrict__ scale, const float* __restrict__ shift,
+              __nv_bfloat16* __restrict__ out, float* __restrict__ se_sum) {
+  extern __shared__ float sse[];  // [C]
+  const int b = blockIdx.y, CV = C >> 3;
+  const int PG = blockDim.x / CV;  // pixel groups in flight
+  const int cv = threadIdx.x % CV, pg = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sse[i] = 0.f;
+  __syncthreads();
+  constexpr int PAD = (K - 1) / 2;
+  const int p_end = min(Ho * Wo, (int)(blockIdx.x + 1) * DW_PIX);
+  float se[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) se[i] = 0.f;
+  if (pg < PG) {
+    const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8)), sc1 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
+    const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8)), sh1 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
+    const __nv_bfloat16* src = in + (size_t)b * H * W * C + cv * 8;
+    for (int p = blockIdx.x * DW_PIX + pg; p < p_end; p += PG) {
+      const int ho = p / Wo, wo = p - ho * Wo;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int hi = ho * stride - PAD + ky;
+        if (hi < 0 || hi >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int wi = wo * stride - PAD + kx;
+          if (wi < 0 || wi >= W) continue;
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)hi * W + wi) * C));
+          const float* wp = wkk + (ky * K + kx) * C + cv * 8;
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          const float2 x0 = __bfloat1622float2(h2[0]), x1 = __bfloat1622float2(h2[1]);
+          const float2 x2 = __bfloat1622float2(h2[2]), x3 = __bfloat1622float2(h2[3]);
+          acc[0] = fmaf(x0.x, w0.x, acc[0]); acc[1] = fmaf(x0.y, w0.y, acc[1]);
+          acc[2] = fmaf(x1.x, w0.z, acc[2]); acc[3] = fmaf(x1.y, w0.w, acc[3]);
+          acc[4] = fmaf(x2.x, w1.x, acc[4]); acc[5] = fmaf(x2.y, w1.y, acc[5]);
+          acc[6] = fmaf(x3.x, w1.z, acc[6]); acc[7] = fmaf(x3.y, w1.w, acc[7]);
+        }
+      }
+      float y[8];
+      y[0] = silu(fmaf(acc[0], sc0.x, sh0.x)); y[1] = silu(fmaf(acc[1], sc0.y, sh0.y));
+      y[2] = silu(fmaf(acc[2], sc0.z, sh0.z)); y[3] = silu(fmaf(acc[3], sc0.w, sh0.w));
+      y[4] = silu(fmaf(acc[4], sc1.x, sh1.x)); y[5] = silu(fmaf(acc[5], sc1.y, sh1.y));
+      y[6] = silu(fmaf(acc[6], sc1.z, sh1.z)); y[7] = silu(fmaf(acc[7], sc1.w, sh1.w));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) se[i] += y[i];
+      *reinterpret_cast<uint4*>(out + ((size_t)b * Ho * Wo + p) * C + cv * 8) =
+          make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+    }
+    if (se_sum != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sse[cv * 8 + i], se[i]);
+    }
+  }
+  if (se_sum != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(se_sum + (size_t)b * C + i, sse[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// squeeze-excitation MLP per clip: s = sigmoid(W2 silu(W1 avg + b1) + b2)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+se_mlp_kernel(const float* __restrict__ se_sum, float inv_hw, int C, int S, const float* __restrict__ w1,
+              const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+              float* __restrict__ se_scale) {
+  extern __shared__ float sm[];  // avg[C], hid[S]
+  float* avg = sm;
+  float* hid = sm + C;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int c = tid; c < C; c += blockDim.x) avg[c] = se_sum[(size_t)b * C + c] * inv_hw;
+  __syncthreads();
+  for (int j = warp; j < S; j += blockDim.x / 32) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + (size_t)j * C + c), avg[c], a);
+    a = warp_sum(a);
+    if (lane == 0) hid[j] = silu(a + __ldg(b1 + j));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float a = __ldg(b2 + c);
+    for (int j = 0; j < S; ++j) a = fmaf(__ldg(w2 + (size_t)c * S + j), hid[j], a);
+    se_scale[(size_t)b * C + c] = 1.0f / (1.0f + __expf(-a));
+  }
+}
+
+// x[b, p, c] *= s[b, c]   (bf16 NHWC, 8 channels per thread)
+__global__ void __launch_bounds__(256)
+se_apply_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ s, long long per_clip_vec, int CV, long long total_vec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per_clip_vec;
+    const int cv = (int)(i % CV);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + (b * CV + cv) * 8)), s1 = __ldg(reinterpret_cast<const float4*>(s + (b * CV + cv) * 8 + 4));
+    uint4 raw = reinterpret_cast<uint4*>(x)[i];
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&raw);
+    float2 a = __bfloat1622float2(h2[0]), bq = __bfloat1622float2(h2[1]), c = __bfloat1622float2(h2[2]), d = __bfloat1622float2(h2[3]);
+    raw = make_uint4(pack_bf16(a.x * s0.x, a.y * s0.y), pack_bf16(bq.x * s0.z, bq.y * s0.w), pack_bf16(c.x * s1.x, c.y * s1.y),
+                     pack_bf16(d.x * s1.z, d.y * s1.w));
+    reinterpret_cast<uint4*>(x)[i] = raw;
+  }
+}
+
+// [B, P, C] fp32 (NHWC) -> [B, C, P] fp32 (NCHW), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ in, int P, int C, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    tile[r][tx] = (p < P && c < C) ? in[((size_t)b * P + p) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (p < P && c < C) out[((size_t)b * C + c) * P + p] = tile[tx][r];
+  }
+}
+
+// global average pool over P then Linear: logits[b, n] = bias[n] + sum_c W[n, c] mean_p x[b, p, c]   (x fp32 NHWC)
+__global__ void __launch_bounds__(256)
+pool_kernel(const float* __restrict__ x, int P, int C, float* __restrict__ pooled) {
+  const int b = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int p = 0; p < P; ++p) a += x[((size_t)b * P + p) * C + c];
+  pooled[(size_t)b * C + c] = a / (float)P;
+}
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int C, int N,
+              float* __restrict__ out) {
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x / 32) + warp;
+  if (n >= N) return;
+  float a = 0.f;
+  for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w + (size_t)n * C + c), x[(size_t)b * C + c], a);
+  a = warp_sum(a);
+  if (lane == 0) out[(size_t)b * N + n] = a + __ldg(bias + n);
+}
+
+template <typename T>
+int dev_alloc(avexk_effnet* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return AVEXK_ECUDA;
+  }
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return AVEXK_OK;
+}
+
+int fold_bn(avexk_effnet* h, const avexk_bn_params& bn, int C, float** scale, float** shift, cudaStream_t st) {
+  int rc = dev_alloc(h, scale, C);
+  if (rc) return rc;
+  rc = dev_alloc(h, shift, C);
+  if (rc) return rc;
+  AVEXK_CHECK_ARG(bn.weight && bn.bias && bn.mean && bn.var, "effnet: missing BatchNorm parameter");
+  bn_fold_kernel<<<ceil_div(C, 256), 256, 0, st>>>(bn.weight, bn.bias, bn.mean, bn.var, 1e-5f, C, *scale, *shift);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+int copy_f32(avexk_effnet* h, float** dst, const float* src, size_t n, cudaStream_t st) {
+  AVEXK_CHECK_ARG(src != nullptr, "effnet: missing parameter tensor");
+  int rc = dev_alloc(h, dst, n);
+  if (rc) return rc;
+  AVEXK_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return AVEXK_OK;
+}
+
+int to_bf16(avexk_effnet* h, __nv_bfloat16** dst, const float* src, size_t n, cudaStream_t st) {
+  AVEXK_CHECK_ARG(src != nullptr, "effnet: missing conv weight");
+  int rc = dev_alloc(h, dst, n);
+  if (rc) return rc;
+  return launch_f32_to_bf16(src, *dst, (long long)n, st);
+}
+
+struct Geom {
+  int H, W;
+};
+inline int conv_out(int n, int k, int stride) { return (n + 2 * ((k - 1) / 2) - k) / stride + 1; }
+
+}  // namespace
+
+int launch_dwconv(const __nv_bfloat16* in, int B, int H, int W, int C, int k, int stride, const float* wkk, const float* scale,
+                  const float* shift, __nv_bfloat16* out, float* se_sum, cudaStream_t st) {
+  AVEXK_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "dwconv: unsupported C=%d k=%d stride=%d", C, k, stride);
+  if (B == 0) return AVEXK_OK;
+  const int Ho = conv_out(H, k, stride), Wo = conv_out(W, k, stride);
+  dim3 grid(ceil_div((long long)Ho * Wo, DW_PIX), B);
+  if (k == 3) dwconv_kernel<3><<<grid, 256, C * sizeof(float), st>>>(in, H, W, C, Ho, Wo, stride, wkk, scale, shift, out, se_sum);
+  else dwconv_kernel<5><<<grid, 256, C * sizeof(float), st>>>(in, H, W, C, Ho, Wo, stride, wkk, scale, shift, out, se_sum);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+}  // namespace avexk
+
+// ============================================================================================================
+// C ABI
+// ============================================================================================================
+extern "C" int avexk_conv1x1_bf16(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift,
+                                  int silu, const void* res_bf16, float* raw_out, void* out, int out_bf16, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(A && W && (out || raw_out) && M >= 0, "avexk_conv1x1_bf16: null argument");
+  return conv1x1_launch(A, W, M, N, K, scale, shift, silu, reinterpret_cast<const __nv_bfloat16*>(res_bf16), raw_out, out, out_bf16,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int avexk_dwconv_nhwc(const void* in_bf16, int B, int H, int W, int C, int k, int stride, const float* w_ckk,
+                                 const float* scale, const float* shift, void* out_bf16, float* se_sum, void* workspace,
+                                 void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(in_bf16 && w_ckk && scale && shift && out_bf16 && workspace, "avexk_dwconv_nhwc: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* wkk = reinterpret_cast<float*>(workspace);  // >= C*k*k floats
+  dw_pack_kernel<<<ceil_div(C * k * k, 256), 256, 0, st>>>(w_ckk, C, k * k, wkk);
+  AVEXK_LAUNCH_CHECK();
+  if (se_sum) AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(float) * (size_t)B * C, st));
+  return launch_dwconv(reinterpret_cast<const __nv_bfloat16*>(in_bf16), B, H, W, C, k, stride, wkk, scale, shift,
+                       reinterpret_cast<__nv_bfloat16*>(out_bf16), se_sum, st);
+}
+
+extern "C" int avexk_effnet_create(const avexk_effnet_block_cfg* blocks, int num_blocks, int stem_out, int head_out,
+                                   avexk_effnet_t** out) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(blocks && num_blocks > 0 && out, "avexk_effnet_create: null argument");
+  AVEXK_CHECK_ARG(stem_out == STEM_C, "avexk_effnet_create: stem kernel is specialised to %d output channels (got %d)", STEM_C, stem_out);
+  AVEXK_CHECK_ARG(head_out % 8 == 0, "avexk_effnet_create: head width must be a multiple of 8");
+  int cin = stem_out;
+  for (int i = 0; i < num_blocks; ++i) {
+    const avexk_effnet_block_cfg& c = blocks[i];
+    AVEXK_CHECK_ARG(c.cin == cin && c.cin % 8 == 0 && c.cexp % 8 == 0 && c.cout % 8 == 0 && c.csq >= 1 && c.cexp <= 2048,
+                    "avexk_effnet_create: block %d has unsupported channels (cin=%d cexp=%d cout=%d csq=%d)", i, c.cin, c.cexp, c.cout, c.csq);
+    AVEXK_CHECK_ARG((c.kernel == 3 || c.kernel == 5) && (c.stride == 1 || c.stride == 2), "avexk_effnet_create: block %d kernel/stride unsupported", i);
+    cin = c.cout;
+  }
+  auto* h = new avexk_effnet();
+  h->cfg.assign(blocks, blocks + num_blocks);
+  h->blocks.resize(num_blocks);
+  h->stem_out = stem_out;
+  h->head_in = cin;
+  h->head_out = head_out;
+  *out = h;
+  return AVEXK_OK;
+}
+
+extern "C" void avexk_effnet_destroy(avexk_effnet_t* h) {
+  if (!h) return;
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int avexk_effnet_load_weights(avexk_effnet_t* h, const avexk_effnet_weights* w, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(h && w && w->blocks, "avexk_effnet_load_weights: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->loaded = false;
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  AVEXK_CHECK_ARG(w->stem_w != nullptr, "avexk_effnet_load_weights: stem weight missing");
+  TRY(dev_alloc(h, &h->stem_w, 9 * h->stem_out));
+  stem_pack_kernel<<<ceil_div(9 * h->stem_out, 256), 256, 0, st>>>(w->stem_w, h->stem_out, h->stem_w);
+  AVEXK_LAUNCH_CHECK();
+  TRY(fold_bn(h, w->stem_bn, h->stem_out, &h->stem_scale, &h->stem_shift, st));
+  for (size_t i = 0; i < h->cfg.size(); ++i) {
+    const avexk_effnet_block_cfg& c = h->cfg[i];
+    const avexk_effnet_block_weights& s = w->blocks[i];
+    avexk_effnet::Block& b = h->blocks[i];
+    b = avexk_effnet::Block();
+    if (c.cexp != c.cin || s.expand_w != nullptr) {
+      TRY(to_bf16(h, &b.expand_w, s.expand_w, (size_t)c.cexp * c.cin, st));
+      TRY(fold_bn(h, s.expand_bn, c.cexp, &b.expand_scale, &b.expand_shift, st));
+    }
+    AVEXK_CHECK_ARG(s.dw_w != nullptr, "avexk_effnet_load_weights: block %zu depthwise weight missing", i);
+    TRY(dev_alloc(h, &b.dw_w, (size_t)c.cexp * c.kernel * c.kernel));
+    dw_pack_kernel<<<ceil_div(c.cexp * c.kernel * c.kernel, 256), 256, 0, st>>>(s.dw_w, c.cexp, c.kernel * c.kernel, b.dw_w);
+    AVEXK_LAUNCH_CHECK();
+    TRY(fold_bn(h, s.dw_bn, c.cexp, &b.dw_scale, &b.dw_shift, st));
+    TRY(copy_f32(h, &b.se1_w, s.se1_w, (size_t)c.csq * c.cexp, st));
+    TRY(copy_f32(h, &b.se1_b, s.se1_b, c.csq, st));
+    TRY(copy_f32(h, &b.se2_w, s.se2_w, (size_t)c.cexp * c.csq, st));
+    TRY(copy_f32(h, &b.se2_b, s.se2_b, c.cexp, st));
+    TRY(to_bf16(h, &b.proj_w, s.proj_w, (size_t)c.cout * c.cexp, st));
+    TRY(fold_bn(h, s.proj_bn, c.cout, &b.proj_scale, &b.proj_shift, st));
+  }
+  TRY(to_bf16(h, &h->head_w, w->head_w, (size_t)h->head_out * h->head_in, st));
+  TRY(fold_bn(h, w->head_bn, h->head_out, &h->head_scale, &h->head_shift, st));
+  h->num_classes = 0;
+  if (w->cls_w != nullptr && w->num_classes > 0) {
+    TRY(copy_f32(h, &h->cls_w, w->cls_w, (size_t)w->num_classes * h->head_out, st));
+    TRY(copy_f32(h, &h->cls_b, w->cls_b, w->num_classes, st));
+    h->num_classes = w->num_classes;
+  }
+#undef TRY
+  AVEXK_CUDA(cudaStreamSynchronize(st));
+  h->loaded = true;
+  return AVEXK_OK;
+}
+
+namespace avexk {
+namespace {
+struct EffPlan {
+  size_t act, exp, dw, raw, se, total;
+  int Hf, Wf;
+};
+EffPlan effnet_plan(const avexk_effnet* h, int B, int H0, int W0) {
+  auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+  EffPlan p{};
+  int H = conv_out(H0, 3, 2), W = conv_out(W0, 3, 2);
+  size_t act = (size_t)H * W * h->stem_out, ex = 0, dw = 0, raw = 0, se = 0;
+  for (const auto& c : h->cfg) {
+    ex = std::max(ex, (size_t)H * W * c.cexp);
+    const int Ho = conv_out(H, c.kernel, c.stride), Wo = conv_out(W, c.kernel, c.stride);
+    dw = std::max(dw, (size_t)Ho * Wo * c.cexp);
+    act = std::max(act, (size_t)Ho * Wo * c.cout);
+    raw = std::max(raw, (size_t)Ho * Wo * c.cout);
+    se = std::max(se, (size_t)c.cexp);
+    H = Ho;
+    W = Wo;
+  }
+  raw = std::max(raw, (size_t)H * W * h->head_out);
+  p.Hf = H;
+  p.Wf = W;
+  p.act = al(act * B * 2);
+  p.exp = al(ex * B * 2);
+  p.dw = al(dw * B * 2);
+  p.raw = al(raw * B * 4);
+  p.se = al(se * B * 4);
+  p.total = 2 * p.act + p.exp + p.dw + 2 * p.raw + 2 * p.se + al((size_t)B * h->head_out * 4) + 4096;
+  return p;
+}
+}  // namespace
+}  // namespace avexk
+
+extern "C" int avexk_effnet_out_hw(const avexk_effnet_t* h, int H0, int W0, int* Hf, int* Wf) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(h && Hf && Wf && H0 > 0 && W0 > 0, "avexk_effnet_out_hw: bad argument");
+  const EffPlan p = effnet_plan(h, 1, H0, W0);
+  *Hf = p.Hf;
+  *Wf = p.Wf;
+  return AVEXK_OK;
+}
+
+extern "C" size_t avexk_effnet_workspace_bytes(const avexk_effnet_t* h, int B, int H0, int W0) {
+  if (!h || B <= 0 || H0 <= 0 || W0 <= 0) return 0;
+  return avexk::effnet_plan(h, B, H0, W0).total;
+}
+
+extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const void* minmax, int B, int H0, int W0,
+                                    float* features_nchw, float* logits, float* const* hook_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(h && h->loaded, "avexk_effnet_forward: weights not loaded");
+  AVEXK_CHECK_ARG(mel && workspace && B > 0 && H0 > 0 && W0 > 0, "avexk_effnet_forward: bad argument");
+  AVEXK_CHECK_ARG(features_nchw || logits || hook_out, "avexk_effnet_forward: no output requested");
+  AVEXK_CHECK_ARG(!logits || h->num_classes > 0, "avexk_effnet_forward: logits requested but no classifier was loaded");
+  AVEXK_CHECK_ARG(B <= 65535, "avexk_effnet_forward: B=%d exceeds grid.y", B);
+  const EffPlan pl = effnet_plan(h, B, H0, W0);
+  AVEXK_CHECK_ARG(workspace_bytes >= pl.total, "avexk_effnet_forward: workspace too small (%zu < %zu)", workspace_bytes, pl.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  char* p = reinterpret_cast<char*>(workspace);
+  __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(p); p += pl.act;
+  __nv_bfloat16* act2 = reinterpret_cast<__nv_bfloat16*>(p); p += pl.act;
+  __nv_bfloat16* ex = reinterpret_cast<__nv_bfloat16*>(p); p += pl.exp;
+  __nv_bfloat16* dw = reinterpret_cast<__nv_bfloat16*>(p); p += pl.dw;
+  float* raw = reinterpret_cast<float*>(p); p += pl.raw;
+  float* raw2 = reinterpret_cast<float*>(p); p += pl.raw;
+  float* se_sum = reinterpret_cast<float*>(p); p += pl.se;
+  float* se_scale = reinterpret_cast<float*>(p); p += pl.se;
+  float* pooled = reinterpret_cast<float*>(p);
+  const int nb = (int)h->cfg.size();
+  int rc;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+  auto to_nchw = [&](const float* src, int P, int C, float* dst) -> int {
+    dim3 grid(ceil_div(P, 32), ceil_div(C, 32), B);
+    nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(src, P, C, dst);
+    AVEXK_LAUNCH_CHECK();
+    return AVEXK_OK;
+  };
+  // ---- stem -------------------------------------------------------------------------------------------------------
+  int H = conv_out(H0, 3, 2), W = conv_out(W0, 3, 2);
+  {
+    dim3 grid(ceil_div((long long)H * W, 256), B);
+    stem_kernel<<<grid, 256, 0, st>>>(mel, reinterpret_cast<const unsigned*>(minmax), B, H0, W0, H, W, h->stem_w, h->stem_scale,
+                                      h->stem_shift, act, hook_out ? hook_out[0] : nullptr);
+    AVEXK_LAUNCH_CHECK();
+  }
+  // ---- MBConv blocks ----------------------------------------------------------------------------------------------
+  for (int i = 0; i < nb; ++i) {
+    const avexk_effnet_block_cfg& c = h->cfg[i];
+    const avexk_effnet::Block& b = h->blocks[i];
+    const long long M = (long long)B * H * W;
+    const __nv_bfloat16* dw_in = act;
+    if (b.expand_w != nullptr) {
+      TRY(conv1x1_launch(act, b.expand_w, (int)M, c.cexp, c.cin, b.expand_scale, b.expand_shift, 1, nullptr, nullptr, ex, 1, st));
+      dw_in = ex;
+    }
+    const int Ho = conv_out(H, c.kernel, c.stride), Wo = conv_out(W, c.kernel, c.stride);
+    AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(float) * (size_t)B * c.cexp, st));
+    TRY(launch_dwconv(dw_in, B, H, W, c.cexp, c.kernel, c.stride, b.dw_w, b.dw_scale, b.dw_shift, dw, se_sum, st));
+    se_mlp_kernel<<<B, 256, (c.cexp + c.csq) * sizeof(float), st>>>(se_sum, 1.0f / (float)(Ho * Wo), c.cexp, c.csq, b.se1_w, b.se1_b,
+                                                                    b.se2_w, b.se2_b, se_scale);
+    AVEXK_LAUNCH_CHECK();
+    {
+      const long long per_clip_vec = (long long)Ho * Wo * (c.cexp / 8), total = per_clip_vec * B;
+      int grid = ceil_div(total, 256);
+      if (grid > 148 * 16) grid = 148 * 16;
+      se_apply_kernel<<<grid, 256, 0, st>>>(dw, se_scale, per_clip_vec, c.cexp / 8, total);
+      AVEXK_LAUNCH_CHECK();
+    }
+    const long long Mo = (long long)B * Ho * Wo;
+    const bool use_res = c.stride == 1 && c.cin == c.cout;
+    float* hook = hook_out ? hook_out[1 + i] : nullptr;
+    TRY(conv1x1_launch(dw, b.proj_w, (int)Mo, c.cout, c.cexp, b.proj_scale, b.proj_shift, 0, use_res ? act : nullptr,
+                       hook ? raw : nullptr, act2, 1, st));
+    if (hook) TRY(to_nchw(raw, Ho * Wo, c.cout, hook));
+    std::swap(act, act2);
+    H = Ho;
+    W = Wo;
+  }
+  // ---- head -------------------------------------------------------------------------------------------------------
+  {
+    const long long M = (long long)B * H * W;
+    float* hook = hook_out ? hook_out[nb + 1] : nullptr;
+    TRY(conv1x1_launch(act, h->head_w, (int)M, h->head_out, h->head_in, h->head_scale, h->head_shift, 1, nullptr,
+                       hook ? raw : nullptr, raw2, 0, st));
+    if (hook) TRY(to_nchw(raw, H * W, h->head_out, hook));
+    if (features_nchw) TRY(to_nchw(raw2, H * W, h->head_out, features_nchw));
+    if (logits) {
+      dim3 g1(ceil_div(h->head_out, 256), B);
+      pool_kernel<<<g1, 256, 0, st>>>(raw2, H * W, h->head_out, pooled);
+      AVEXK_LAUNCH_CHECK();
+      dim3 g2(ceil_div(h->num_classes, 8), B);
+      linear_kernel<<<g2, 256, 0, st>>>(pooled, h->cls_w, h->cls_b, h->head_out, h->num_classes, logits);
+      AVEXK_LAUNCH_CHECK();
+    }
+  }
+#undef TRY
+  return AVEXK_OK;
+}

@@ -37,20 +37,49 @@ struct GemmArgs {
   void* out;
   long long ldo;
   int out_bf16;
+  // conv mode (EfficientNet 1x1 convolutions): y = act(acc * scale[n] + bias[n]) (+ res_bf16), raw_out = acc
+  const float* scale;
+  int silu;
+  const __nv_bfloat16* res_bf16;
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7): exact-GELU (modules.py:191-200) well inside bf16 rounding.
-__device__ __forceinline__ float gelu_fast(float v) {
-  const float z = fabsf(v) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|v|/sqrt2)
-  return 0.5f * v * (1.0f + copysignf(e, v));
+// Exact GELU (modules.py:191-200) for two values per call with packed fp32x2 arithmetic.  erf via Abramowitz-Stegun
+// 7.1.26 (|err| < 1.5e-7, far inside the bf16 rounding of the output).  With a = |v|, z = a / sqrt(2) and
+// E(z) = erf(z) = 1 - P(t) e^{-z^2}, t = 1 / (1 + p z):   gelu(v) = 0.5 v + 0.5 a E(z)   (v erf(v/sqrt2) = a E(z)).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 gelu_fast2(float2 v) {
+  const float2 a = make_float2(fabsf(v.x), fabsf(v.y));
+  const float2 d = __ffma2_rn(a, make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f),
+                              make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  p = __fmul2_rn(p, t);
+  // e^{-z^2} = 2^{-(a k)^2}, k = sqrt(log2(e) / 2)
+  constexpr float k = 0.84932180028801904272f;
+  const float2 zk = __fmul2_rn(a, make_float2(k, k)), nzk = __fmul2_rn(a, make_float2(-k, -k));
+  const float2 q = __fmul2_rn(zk, nzk);
+  const float2 pe = __fmul2_rn(p, make_float2(ex2_approx(q.x), ex2_approx(q.y)));
+  const float2 ha = __fmul2_rn(a, make_float2(0.5f, 0.5f)), nha = __fmul2_rn(a, make_float2(-0.5f, -0.5f));
+  const float2 s = __ffma2_rn(nha, pe, ha);  // 0.5 a E(z)
+  return __ffma2_rn(v, make_float2(0.5f, 0.5f), s);
 }
 
+// CONV = false: BEATs epilogue (bias, GELU, raw store, fp32 residual * alpha).  CONV = true: folded-BatchNorm epilogue of
+// a 1x1 convolution in NHWC (raw pre-BN store, per-channel scale + shift, SiLU, bf16 residual); K and N need only be
+// multiples of 8: the TMA maps zero-fill the out-of-range part of the last K block / N tile.
+template <bool CONV>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
@@ -67,7 +96,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (g.M + BM - 1) / BM, n_blocks = (g.N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks, num_kb = g.K / BK;
+  const int num_tiles = m_blocks * n_blocks, num_kb = (g.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -144,7 +173,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
     float* stg = stg_base + ew * (32 * 32);
     const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
-    const bool has_res = g.residual != nullptr;
+    const bool has_res = !CONV && g.residual != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     float4 res_next[8];
@@ -188,21 +217,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
           __syncwarp();
           const int cc = col0 + csub * 4;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
           if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+          if (CONV && g.scale != nullptr && cc < g.N) scale4 = __ldg(reinterpret_cast<const float4*>(g.scale + cc));
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;
             const int grow = row0 + rr;
             if (grow < g.M && cc < g.N) {
               float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((csub ^ (rr & 7)) << 2));
-              v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-              if (g.gelu) { v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w); }
               const size_t off = (size_t)grow * g.N + cc;
-              if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
-              if (has_res) {
-                v.x = fmaf(g.res_scale, res_cur[it].x, v.x); v.y = fmaf(g.res_scale, res_cur[it].y, v.y);
-                v.z = fmaf(g.res_scale, res_cur[it].z, v.z); v.w = fmaf(g.res_scale, res_cur[it].w, v.w);
+              if (CONV) {
+                if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;  // pre-BN conv output (hook)
+                v.x = fmaf(v.x, scale4.x, bias4.x); v.y = fmaf(v.y, scale4.y, bias4.y);
+                v.z = fmaf(v.z, scale4.z, bias4.z); v.w = fmaf(v.w, scale4.w, bias4.w);
+                if (g.silu) {
+                  v.x *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.x));
+                  v.y *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.y));
+                  v.z *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.z));
+                  v.w *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.w));
+                }
+                if (g.res_bf16 != nullptr) {
+                  const uint2 rb = __ldg(reinterpret_cast<const uint2*>(g.res_bf16 + off));
+                  const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.x));
+                  const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.y));
+                  v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
+                }
+              } else {
+                v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                if (g.gelu) {
+                  const float2 g0 = gelu_fast2(make_float2(v.x, v.y)), g1 = gelu_fast2(make_float2(v.z, v.w));
+                  v = make_float4(g0.x, g0.y, g1.x, g1.y);
+                }
+                if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
+                if (has_res) {
+                  v.x = fmaf(g.res_scale, res_cur[it].x, v.x); v.y = fmaf(g.res_scale, res_cur[it].y, v.y);
+                  v.z = fmaf(g.res_scale, res_cur[it].z, v.z); v.w = fmaf(g.res_scale, res_cur[it].w, v.w);
+                }
               }
               if (g.out != nullptr) {
                 const size_t oo = (size_t)grow * g.ldo + cc;
@@ -241,14 +292,40 @@ int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
                      cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  GemmArgs g{M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16};
+  GemmArgs g{M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16, nullptr, 0, nullptr};
   const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   prof_begin(st, KID_GEMM, 2.0 * M * N * K);
-  gemm_bf16_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, g);
+  gemm_bf16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, g);
+  prof_end(st);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long long lda, const void* W, long long ldw, int M,
+                   int N, int K);
+
+// 1x1 convolution in NHWC: out[M, N] = act((A[M, K] @ W[N, K]^T) * scale + shift) (+ res); K, N multiples of 8.
+int conv1x1_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
+                   const __nv_bfloat16* res, float* raw_out, void* out, int out_bf16, cudaStream_t st) {
+  AVEXK_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && K > 0 && N > 0, "conv1x1: channel counts must be multiples of 8 (K=%d N=%d)", K, N);
+  if (M == 0) return AVEXK_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ma, mb;
+  int rc = gemm_make_maps(&ma, &mb, A, K, W, K, M, N, K);
+  if (rc) return rc;
+  GemmArgs g{M, N, K, shift, 0, raw_out, nullptr, 0.f, out, N, out_bf16, scale, silu, res};
+  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  prof_begin(st, KID_GEMM, 2.0 * M * N * K);
+  gemm_bf16_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, g);
   prof_end(st);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
@@ -268,7 +345,7 @@ extern "C" int avexk_gemm_bf16(const void* A, long long lda, const void* W, long
                                long long ldo, int out_bf16, void* stream) {
   using namespace avexk;
   AVEXK_CHECK_ARG(A && W && (out || raw_out), "avexk_gemm_bf16: null operand");
-  AVEXK_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % 64 == 0 && N % 16 == 0, "avexk_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
+  AVEXK_CHECK_ARG(M >= 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, "avexk_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
   AVEXK_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0 && (out == nullptr || (ldo >= N && ldo % 8 == 0)),
                   "avexk_gemm_bf16: bad leading dimensions");
   if (M == 0) return AVEXK_OK;

@@ -12,6 +12,8 @@ int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long l
 int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, int gelu,
                      float* raw_out, const float* residual, float res_scale, void* out, long long ldo, int out_bf16,
                      cudaStream_t st);
+int conv1x1_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
+                   const __nv_bfloat16* res, float* raw_out, void* out, int out_bf16, cudaStream_t st);
 // elementwise.cu
 int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, float* out_f32,
                      void* out_bf16, cudaStream_t st, int split3 = 0);

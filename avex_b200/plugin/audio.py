@@ -19,10 +19,17 @@ class AudioProcessor:
         self.n_mels = cfg.n_mels
         self.normalize = cfg.normalize
         self.target_length_seconds = cfg.target_length_seconds
+        self._mel = None
 
     def __call__(self, waveform: torch.Tensor) -> torch.Tensor:
         if self.representation == "raw":
             return waveform
+        if self.representation == "mel_spectrogram" and (self.n_fft, self.hop_length, self.win_length, self.n_mels) == (800, 160, 800, 128):
+            if self._mel is None:
+                from ..melspec import MelSpectrogram
+
+                self._mel = MelSpectrogram()
+            return self._mel.run(waveform, normalize=bool(self.normalize))  # [B, 128, frames], audio_utils.py:137-155
         raise NotImplementedError(
             f"avex_b200: representation {self.representation!r} is not on the BEATs hot path "
             "(the EfficientNet mel front end has its own kernel entry point)"

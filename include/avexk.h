@@ -81,7 +81,8 @@ int avexk_fbank_forward(const avexk_fbank_t* h, const float* wav, int B, int T, 
  *   if raw_out:   raw_out[m,n] = v   (fp32; the tensor a forward hook on the Linear would see)
  *   if residual:  v = v + res_scale * residual[m,n]  (fp32 residual; backbone.py:360, :372)
  *   out[m,n] = v  as fp32 (out_bf16 == 0) or bf16    (out may be NULL when only raw_out is wanted)
- * Requirements: K % 64 == 0, N % 16 == 0, all pointers 16-byte aligned, ld* % 8 == 0. */
+ * Requirements: K % 8 == 0, N % 8 == 0 (TMA zero-fills the ragged last K block / N tile), all pointers 16-byte aligned,
+ * ld* % 8 == 0. */
 int avexk_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
                     int gelu, float* raw_out, const float* residual, float res_scale, void* out, long long ldo,
                     int out_bf16, void* stream);
@@ -171,6 +172,101 @@ size_t avexk_beats_workspace_bytes(const avexk_beats_t* h, int B, int T);
 int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, int T, long long wav_stride,
                         const avexk_fbank_t* fbank, const uint8_t* key_pad, const float* bias_vec, float* out,
                         float* const* hook_out, float* pooled, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * STFT mel spectrogram of the EfficientNet path.
+ * Replaces `AudioProcessor.__call__` / `_normalize` (avex/data/audio_utils.py:106-172) for the configuration of
+ *   api/configs/official_models/esp_aves2_effnetb0_all.yml: n_fft = win = 800, hop 160, hann (periodic), center=True
+ *   (reflect pad 400), power spectrogram, 128 HTK mel bins 0..8 kHz (torchaudio MelScale, norm=None), log(x + 1e-6),
+ *   per-clip min-max.  Geometry is fixed to those values.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct avexk_melspec avexk_melspec_t;
+
+/* window_host[800] = torch.hann_window(800); mel_fb_host[401*128] row-major [fft_bin][mel_bin] =
+ * torchaudio.functional.melscale_fbanks(401, 0, 8000, 128, 16000) -- HOST arrays built by the caller with the
+ * reference's own ops (audio_utils.py:97-101, :165); the library derives the sparse per-filter bin ranges and the
+ * double-precision DFT twiddles. */
+int avexk_melspec_create(const float* window_host, const float* mel_fb_host, avexk_melspec_t** out);
+void avexk_melspec_destroy(avexk_melspec_t* h);
+/* frames = 1 + T / 160 (torch.stft, center=True); T must exceed 400 (reflect padding). */
+int avexk_melspec_num_frames(int T);
+/* wav [B,T] fp32 (row stride wav_stride) -> out [B,128,frames] fp32 (frequency-major, time last, as the reference).
+ * minmax_ws: B*2 uint32 device words, receives the per-clip min / max of log(mel + 1e-6) in an order-preserving
+ *   encoding (consumed by avexk_effnet_forward); may be NULL when normalize == 0.
+ * normalize != 0: out = (y - min) / (max - min + 1e-8) per clip (audio_utils.py:167-172); otherwise out = y. */
+int avexk_melspec_forward(const avexk_melspec_t* h, const float* wav, int B, int T, long long wav_stride, int normalize,
+                          float* out, void* minmax_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * EfficientNet building blocks (NHWC bf16 activations) and the whole feature extractor
+ * (avex/models/efficientnet.py:163-215 -> torchvision efficientnet_b0/b1 .features / .avgpool / .classifier).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* 1x1 convolution == GEMM on the tcgen05 kernel: A [M,K] bf16 (NHWC rows), W [N,K] bf16 (conv weight [N,K,1,1]).
+ *   acc = A @ W^T ; raw_out[m,n] = acc (fp32, the pre-BatchNorm tensor a hook on the conv sees; may be NULL)
+ *   y = acc * scale[n] + shift[n] (folded BatchNorm; scale NULL = 1) ; silu != 0: y = y * sigmoid(y)
+ *   res_bf16 != NULL: y += res[m,n] (MBConv skip connection) ; out[m,n] = y as bf16 (out_bf16 != 0) or fp32.
+ * K and N must be multiples of 8. */
+int avexk_conv1x1_bf16(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
+                       const void* res_bf16, float* raw_out, void* out, int out_bf16, void* stream);
+
+/* Depthwise k x k convolution (k = 3 | 5, stride 1 | 2, padding (k-1)/2) + folded BatchNorm + SiLU.
+ * in [B,H,W,C] bf16, w_ckk [C,1,k,k] fp32 (torch layout), out [B,Ho,Wo,C] bf16, Ho = (H + 2p - k) / stride + 1.
+ * se_sum [B,C] fp32 (may be NULL) receives sum over output pixels of the activated output (squeeze-excitation).
+ * workspace >= C*k*k floats (repacked weights). */
+int avexk_dwconv_nhwc(const void* in_bf16, int B, int H, int W, int C, int k, int stride, const float* w_ckk,
+                      const float* scale, const float* shift, void* out_bf16, float* se_sum, void* workspace, void* stream);
+
+typedef struct avexk_effnet avexk_effnet_t;
+
+typedef struct {
+  int kernel, stride; /* depthwise conv */
+  int cin, cexp, cout, csq; /* block input, expanded, output and squeeze channels (cexp == cin: no expand conv) */
+} avexk_effnet_block_cfg;
+
+typedef struct {
+  const float *weight, *bias, *mean, *var; /* BatchNorm2d weight, bias, running_mean, running_var (eps 1e-5) */
+} avexk_bn_params;
+
+/* fp32 DEVICE pointers in torchvision's own layouts (state_dict names relative to `features.{s}.{r}.block`). */
+typedef struct {
+  const float* expand_w;      /* 0.0.weight [cexp,cin,1,1] (NULL when the block has no expand conv)        */
+  avexk_bn_params expand_bn;  /* 0.1.*                                                                      */
+  const float* dw_w;          /* depthwise conv weight [cexp,1,k,k]                                         */
+  avexk_bn_params dw_bn;
+  const float *se1_w, *se1_b; /* SqueezeExcitation fc1 [csq,cexp,1,1], bias                                 */
+  const float *se2_w, *se2_b; /* fc2 [cexp,csq,1,1], bias                                                   */
+  const float* proj_w;        /* project conv [cout,cexp,1,1]  (the `block.3.0` / `block.2.0` hook layer)   */
+  avexk_bn_params proj_bn;
+} avexk_effnet_block_weights;
+
+typedef struct {
+  const float* stem_w;    /* features.0.0.weight [32,3,3,3] */
+  avexk_bn_params stem_bn;
+  const avexk_effnet_block_weights* blocks; /* HOST array, one entry per MBConv block in forward order */
+  const float* head_w;    /* features.8.0.weight [1280,320,1,1] */
+  avexk_bn_params head_bn;
+  const float *cls_w, *cls_b; /* classifier.1 Linear [num_classes,1280] (NULL: features only) */
+  int num_classes;
+} avexk_effnet_weights;
+
+int avexk_effnet_create(const avexk_effnet_block_cfg* blocks, int num_blocks, int stem_out, int head_out, avexk_effnet_t** out);
+void avexk_effnet_destroy(avexk_effnet_t* h);
+/* Folds every BatchNorm into scale / shift, sums the stem weights over the 3 identical input channels
+ * (efficientnet.py:138-140), repacks depthwise weights, converts 1x1 weights to bf16.  Synchronises. */
+int avexk_effnet_load_weights(avexk_effnet_t* h, const avexk_effnet_weights* w, void* stream);
+/* spatial size of the final feature map for an input image of H0 x W0 (128 x frames) */
+int avexk_effnet_out_hw(const avexk_effnet_t* h, int H0, int W0, int* Hf, int* Wf);
+size_t avexk_effnet_workspace_bytes(const avexk_effnet_t* h, int B, int H0, int W0);
+
+/* mel [B,H0,W0] fp32: the single-channel image (log-mel, frequency-major).  minmax != NULL: the image is the
+ * un-normalised output of avexk_melspec_forward(normalize=0) and the per-clip min-max normalisation is applied on load.
+ * features_nchw [B,head_out,Hf,Wf] fp32 (return_features_only) and / or logits [B,num_classes]; either may be NULL.
+ * hook_out: HOST array of num_blocks+2 DEVICE pointers (NULL entry = not materialised), fp32 NCHW pre-BatchNorm conv
+ *   outputs: [0] stem conv (features.0.0), [1+i] project conv of block i, [num_blocks+1] head conv (features.8.0). */
+int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const void* minmax, int B, int H0, int W0,
+                         float* features_nchw, float* logits, float* const* hook_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

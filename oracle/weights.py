@@ -82,3 +82,56 @@ def make_beats_weights(dims: BeatsDims = BeatsDims(), seed: int = 1, init: str =
         W[f"{p}.fc2.bias"] = bias(C)
         W[f"{p}.final_layer_norm.weight"], W[f"{p}.final_layer_norm.bias"] = ln(C)
     return W
+
+
+def make_effnet_weights(seed: int = 3, num_classes: int = 0, bn_stats: dict | None = None) -> dict:
+    """Deterministic synthetic EfficientNet-B0 weights with torchvision's state_dict keys (prefix `model.`, as
+    avex/models/efficientnet.py:61-66 holds the network).  Conv weights: fan-out normal (torchvision's init,
+    efficientnet.py `_efficientnet` -> kaiming_normal_ fan_out); BatchNorm affine mildly perturbed so it is observable.
+    BatchNorm running statistics: `bn_stats` (tests/golden/effnet_bn_stats.npz, the calibration pass of
+    tests/golden/make_golden_effnet.py -- a random network with mean 0 / var 1 statistics collapses to 1e-13 at the
+    head) or the identity statistics when None."""
+    from .effnet import B0_STAGES, HEAD_OUT, STEM_OUT, block_list
+
+    rs = np.random.RandomState(seed)
+    W: dict = {}
+
+    def conv(name, co, ci, k):
+        std = math.sqrt(2.0 / (co * k * k))
+        W[name + ".weight"] = (rs.standard_normal((co, ci, k, k)) * std).astype(np.float32)
+
+    def bnorm(name, c):
+        W[name + ".weight"] = (1.0 + 0.1 * rs.standard_normal(c)).astype(np.float32)
+        W[name + ".bias"] = (0.1 * rs.standard_normal(c)).astype(np.float32)
+        if bn_stats is not None:
+            W[name + ".running_mean"] = np.asarray(bn_stats[name + ".running_mean"], np.float32)
+            W[name + ".running_var"] = np.asarray(bn_stats[name + ".running_var"], np.float32)
+        else:
+            W[name + ".running_mean"] = np.zeros(c, np.float32)
+            W[name + ".running_var"] = np.ones(c, np.float32)
+        W[name + ".num_batches_tracked"] = np.zeros((), np.int64)
+
+    conv("model.features.0.0", STEM_OUT, 3, 3)
+    bnorm("model.features.0.1", STEM_OUT)
+    for prefix, k, _s, cin, cexp, cout, csq in block_list(B0_STAGES):
+        j = 0
+        if cexp != cin:
+            conv(f"{prefix}.0.0", cexp, cin, 1)
+            bnorm(f"{prefix}.0.1", cexp)
+            j = 1
+        conv(f"{prefix}.{j}.0", cexp, 1, k)
+        bnorm(f"{prefix}.{j}.1", cexp)
+        conv(f"{prefix}.{j + 1}.fc1", csq, cexp, 1)
+        W[f"{prefix}.{j + 1}.fc1.bias"] = (0.1 * rs.standard_normal(csq)).astype(np.float32)
+        conv(f"{prefix}.{j + 1}.fc2", cexp, csq, 1)
+        W[f"{prefix}.{j + 1}.fc2.bias"] = (0.1 * rs.standard_normal(cexp)).astype(np.float32)
+        conv(f"{prefix}.{j + 2}.0", cout, cexp, 1)
+        bnorm(f"{prefix}.{j + 2}.1", cout)
+    hp = f"model.features.{len(B0_STAGES) + 1}"
+    conv(hp + ".0", HEAD_OUT, B0_STAGES[-1][4], 1)
+    bnorm(hp + ".1", HEAD_OUT)
+    if num_classes:
+        bound = 1.0 / math.sqrt(num_classes)
+        W["model.classifier.1.weight"] = rs.uniform(-bound, bound, size=(num_classes, HEAD_OUT)).astype(np.float32)
+        W["model.classifier.1.bias"] = (0.1 * rs.standard_normal(num_classes)).astype(np.float32)
+    return W

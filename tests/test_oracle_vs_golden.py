@@ -130,3 +130,48 @@ def test_torch_flavour_of_the_oracle(cname):
     out = OT.beats_forward(OT.to_torch(W), torch.from_numpy(case["wav"]), case.get("mask"), dims)
     np.testing.assert_allclose(out["x"].numpy(), g["final"], atol=2e-4, rtol=1e-4)
     np.testing.assert_allclose(out["hook0"].numpy(), g["hook0"], atol=1e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# EfficientNet path: mel front end and CNN oracle vs the reference's own outputs (tests/golden/make_golden_effnet.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_melspec_oracle_vs_reference(golden_dir):
+    from oracle import melspec as OM
+
+    z = np.load(os.path.join(golden_dir, "effnet_mel.npz"))
+    for case in ("noise_2x1s", "tones_2x1s", "noise_1x5s", "ragged_1x8123"):
+        wav, ref = z[case + "__wav"], z[case + "__mel"]
+        got = OM.mel_spectrogram(wav)
+        assert got.shape == ref.shape
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 5e-5, case  # tones: the fp32 reference itself is 1.8e-5 from float64
+        assert np.abs(got - ref).max() <= 5e-4, case  # the reference's own fp32 noise in low-energy bins
+
+
+def test_effnet_oracle_vs_reference(golden_dir):
+    from oracle import effnet as OEF
+    from oracle import melspec as OM
+    from oracle.weights import make_effnet_weights
+
+    stats = dict(np.load(os.path.join(golden_dir, "effnet_bn_stats.npz")))
+    W = make_effnet_weights(seed=3, bn_stats=stats)
+    z = np.load(os.path.join(golden_dir, "effnet_fwd_tones_1x2s.npz"))
+    assert list(z["layer_names"]) == OEF.hook_layer_names()
+    out = OEF.forward(W, OM.mel_spectrogram(z["wav"]))
+    assert out["features"].shape == z["features"].shape
+    assert np.abs(out["features"] - z["features"]).max() <= 2e-3
+    for n in z["layer_names"]:
+        ref = z["hook__" + n].astype(np.float64)
+        tol = 2e-3 if z["hook__" + n].dtype == np.float32 else 2e-2  # large hooks are stored as fp16
+        assert np.abs(out["hooks"][n] - ref).max() <= tol * max(1.0, np.abs(ref).max()), n
+
+
+def test_effnet_oracle_logits_vs_reference(golden_dir):
+    from oracle import effnet as OEF
+    from oracle import melspec as OM
+    from oracle.weights import make_effnet_weights
+
+    stats = dict(np.load(os.path.join(golden_dir, "effnet_bn_stats.npz")))
+    W = make_effnet_weights(seed=3, num_classes=10, bn_stats=stats)
+    z = np.load(os.path.join(golden_dir, "effnet_logits.npz"))
+    out = OEF.forward(W, OM.mel_spectrogram(z["wav"]), want_logits=True)
+    assert np.abs(out["logits"] - z["logits"]).max() <= 2e-3
