@@ -92,7 +92,8 @@ size_t workspace_bytes(const avexk_beats_dims& d, int B, int T) {
   s += al(M * 3 * C * 2);               // qkv
   s += al(M * C * 2);                   // att
   s += al(M * Ff * 2);                  // h
-  s += al(M * C * 4);                   // tmp
+  s += al(M * C * 4);                   // tmp: pre-LN sums (pos-conv; GEMM epilogues when the LayerNorm is not fused)
+  s += al((long long)gemm_ln_scratch_bytes((int)M));  // fused GEMM+LayerNorm: per-CTA tiles, row statistics, counters
   return s + 4096;
 }
 
@@ -216,6 +217,8 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   __nv_bfloat16* att = cw.take<__nv_bfloat16>((size_t)M * C);
   __nv_bfloat16* hb = cw.take<__nv_bfloat16>((size_t)M * Ff);
   float* tmp = cw.take<float>((size_t)M * C);
+  const size_t ln_ws_bytes = gemm_ln_scratch_bytes((int)M);
+  char* ln_ws = cw.take<char>(ln_ws_bytes);
   AVEXK_CHECK_ARG(cw.ok, "avexk_beats_forward: workspace carve failed");
   float* x0 = (hook_out && hook_out[0]) ? hook_out[0] : x0_ws;
 
@@ -223,10 +226,22 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
   auto gemm = [&](const void* A, int K, const __nv_bfloat16* W, int Nn, const float* bias, int gelu, float* raw, const float* res,
                   float rs, void* o, int obf) -> int {
-    CUtensorMap ma, mb;
-    int r = gemm_make_maps(&ma, &mb, A, K, W, K, (int)M, Nn, K);
+    return gemm_bf16_launch(A, K, W, K, (int)M, Nn, K, bias, gelu, raw, res, rs, o, Nn, obf, st);
+  };
+  // GEMM + DeepNorm residual + LayerNorm in one launch when the width matches the fused epilogue (BEATs-base: 768)
+  const bool fuse_ln = C == 768;
+  int ln_first = 1;  // the scratch counters are zeroed once per forward; every launch leaves them zero
+  auto gemm_ln = [&](const void* A, int K, const __nv_bfloat16* W, const float* bias, float* raw, const float* gamma, const float* beta,
+                     float* dst_f32, __nv_bfloat16* dst_bf16) -> int {
+    if (fuse_ln) {
+      const int zero = ln_first;
+      ln_first = 0;
+      return gemm_bf16_ln_launch(A, K, W, K, (int)M, K, bias, raw, x, alpha, gamma, beta, d.ln_eps, dst_f32, dst_bf16, ln_ws, ln_ws_bytes,
+                                 zero, st);
+    }
+    int r = gemm_bf16_launch(A, K, W, K, (int)M, C, K, bias, 0, raw, x, alpha, tmp, C, 0, st);
     if (r) return r;
-    return gemm_bf16_launch(ma, mb, (int)M, Nn, K, bias, gelu, raw, res, rs, o, Nn, obf, st);
+    return launch_layernorm(tmp, (int)M, C, gamma, beta, d.ln_eps, dst_f32, dst_bf16, st);
   };
 
   // ---- front end: fbank -> patch embed -> LN -> post_extract_proj (beats.py:344-359) -----------------------------
@@ -245,13 +260,11 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
     const bool last = li == d.layers - 1;
     TRY(gemm(xb, C, L.qkv_w, 3 * C, L.qkv_b, 0, nullptr, nullptr, 0.f, qkv, 1));
     TRY(avexk_attention_gated(qkv, B, N, H, L.gate_w, L.gate_b, L.grep_a, bias_vec, key_pad, att, stream));
-    TRY(gemm(att, C, L.o_w, C, L.o_b, 0, nullptr, x, alpha, tmp, 0));
-    TRY(launch_layernorm(tmp, (int)M, C, L.ln1_w, L.ln1_b, d.ln_eps, x, xb, st));
+    TRY(gemm_ln(att, C, L.o_w, L.o_b, nullptr, L.ln1_w, L.ln1_b, x, xb));
     TRY(gemm(xb, C, L.fc1_w, Ff, L.fc1_b, 1, nullptr, nullptr, 0.f, hb, 1));
     float* raw = hook_out ? hook_out[li + 1] : nullptr;
-    TRY(gemm(hb, Ff, L.fc2_w, C, L.fc2_b, 0, raw, x, alpha, tmp, 0));
     float* dst = (last && out) ? out : x;
-    TRY(launch_layernorm(tmp, (int)M, C, L.ln2_w, L.ln2_b, d.ln_eps, dst, last ? nullptr : xb, st));
+    TRY(gemm_ln(hb, Ff, L.fc2_w, L.fc2_b, raw, L.ln2_w, L.ln2_b, dst, last ? nullptr : xb));
     if (last && pooled) {
       // any_pad is decided on the host by the caller passing key_pad == NULL when nothing is padded
       TRY(launch_mean_pool(dst, key_pad, key_pad != nullptr, B, N, C, pooled, st));

@@ -4,15 +4,26 @@
 //
 // Replaces every nn.Linear on the BEATs path (backbone.py:531-533 q/k/v, :572 out_proj, :365-370 fc1/fc2,
 // beats.py:350 patch-embed as im2col GEMM, :359 post_extract_proj) and the elementwise ops that follow them
-// (bias, exact GELU, DeepNorm residual `residual * alpha + x`, backbone.py:360,:372), fused in the epilogue.
+// (bias, exact GELU, DeepNorm residual `residual * alpha + x`, backbone.py:360,:372, and the post-LN LayerNorm of
+// backbone.py:362,:373), fused in the epilogue.  Also the 1x1 convolutions of EfficientNet (MODE_CONV).
 //
-// Structure (one CTA per SM, 320 threads):
-//   warp 0      TMA producer : cp.async.bulk.tensor 128x64 (A) + 256x64 (W) bf16 tiles, 128B swizzle, 4-stage ring
-//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma 128x256x16 (cta_group::1), commits to mbarriers
-//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 from TMEM -> registers -> per-warp smem transposition ->
-//                              coalesced 16-byte global stores; the fp32 residual is register-prefetched one chunk ahead
+// Structure (one CTA per SM, 320 threads; PAIR = two CTAs of a cluster drive one 256x256 tile with cta_group::2):
+//   warp 0      TMA producer : cp.async.bulk.tensor 128x64 (A) + 256x64 (W; 128x64 per CTA of a pair) bf16 tiles,
+//                              128B swizzle, 4-stage (6-stage for a pair) mbarrier ring
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma 128x256x16 (cta_group::1) or 256x256x16
+//                              (cta_group::2, leader CTA only; each CTA holds half of W's rows, so the shared-memory
+//                              operand traffic per SM drops from 96 to 64 bytes/clk), commits to mbarriers
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 from TMEM (next chunk in flight while this one is processed) ->
+//                              per-warp smem transposition -> coalesced 16-byte global stores; the fp32 residual is
+//                              register-prefetched one chunk ahead
 //   TMEM: 512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Fused LayerNorm (MODE_RES, N == 768): a CTA walks the three 256-column tiles of a 128-row block back to back, parks
+// the pre-LN sums in a per-CTA scratch that stays L2-resident (148 x 393 KB), and its epilogue warps normalise the
+// rows from L2 while the tensor core is already on the next row block: the [M,768] fp32 pre-LN tensor never makes the
+// round trip through HBM and the separate LayerNorm launch disappears.
 // Roofline: dense bf16 tensor pipe; algorithmic FLOPs = 2*M*N*K.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
@@ -20,32 +31,50 @@
 namespace avexk {
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 8;
-constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;                // 32 rows x 32 fp32, XOR-swizzled (no padding)
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 256;
-constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int CTRL_WARPS = 4;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle (register donors: setmaxnreg works per warpgroup)
+constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
+constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;  // 32 rows x 32 fp32, XOR-swizzled (no padding)
+constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS);
+constexpr int CTRL_REGS = 64, EPI_REGS = 216;  // 128 * 64 + 256 * 216 = 63488 <= 65536
+constexpr int LN_C = 768, LN_NB = LN_C / BN;   // the fused LayerNorm epilogue is built for rows of 3 tiles
+
+template <bool PAIR>
+struct Cfg {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of W each CTA stages per k-block
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TX_BYTES = STAGE_BYTES * (PAIR ? 2 : 1);  // bytes landing on the (leader's) full barrier
+  static constexpr int UM = PAIR ? 2 * BM : BM;                  // output rows per scheduling unit
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 256 + BM * 8;
+};
+
+enum { MODE_PLAIN = 0, MODE_GELU = 1, MODE_RES = 2, MODE_CONV = 3 };
 
 struct GemmArgs {
   int M, N, K;
   const float* bias;
-  int gelu;
   float* raw_out;
   const float* residual;
   float res_scale;
   void* out;
   long long ldo;
   int out_bf16;
-  // conv mode (EfficientNet 1x1 convolutions): y = act(acc * scale[n] + bias[n]) (+ res_bf16), raw_out = acc
+  // MODE_CONV (EfficientNet 1x1 convolutions): y = act(acc * scale[n] + bias[n]) (+ res_bf16), raw_out = acc
   const float* scale;
   int silu;
   const __nv_bfloat16* res_bf16;
+  // fused LayerNorm (MODE_RES, N == 768)
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  float* ln_out_f32;
+  __nv_bfloat16* ln_out_bf16;
+  float* ln_tiles;   // [gridDim.x][128][256] fp32: this CTA's pre-LN tile, re-read from L2 a few microseconds later
+  float2* ln_stats;  // [ceil(M/128)*128][2*LN_NB] (sum, sum of squares) over 128 columns of a row
+  int* ln_count;     // [2][ceil(M/128)]: arrivals / departures per 128-row block; zero before and after every launch
 };
 
-// Exact GELU (modules.py:191-200) for two values per call with packed fp32x2 arithmetic.  erf via Abramowitz-Stegun
-// 7.1.26 (|err| < 1.5e-7, far inside the bf16 rounding of the output).  With a = |v|, z = a / sqrt(2) and
-// E(z) = erf(z) = 1 - P(t) e^{-z^2}, t = 1 / (1 + p z):   gelu(v) = 0.5 v + 0.5 a E(z)   (v erf(v/sqrt2) = a E(z)).
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -56,49 +85,69 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// Exact (erf) GELU (modules.py:191-200) for two values per call with packed fp32x2 arithmetic and ONE special-function
+// op per value.  With a = |v|:  gelu(v) = v Phi(v) = relu(v) - a * (erfc(a / sqrt2) / 2), and log2(erfc(a / sqrt2) / 2)
+// is smooth, so a degree-5 polynomial q (least-squares fit of a 2^q(a) on [0, 6], leading coefficient negative so the
+// tail decays) reproduces GELU to |err| <= 6.5e-7 over the whole real line -- three decimal orders inside the bf16
+// rounding of the stored activation.  Evaluated in n = -a so the final product needs no negation.
 __device__ __forceinline__ float2 gelu_fast2(float2 v) {
-  const float2 a = make_float2(fabsf(v.x), fabsf(v.y));
-  const float2 d = __ffma2_rn(a, make_float2(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f),
-                              make_float2(1.0f, 1.0f));
-  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
-  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
-  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
-  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
-  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
-  p = __fmul2_rn(p, t);
-  // e^{-z^2} = 2^{-(a k)^2}, k = sqrt(log2(e) / 2)
-  constexpr float k = 0.84932180028801904272f;
-  const float2 zk = __fmul2_rn(a, make_float2(k, k)), nzk = __fmul2_rn(a, make_float2(-k, -k));
-  const float2 q = __fmul2_rn(zk, nzk);
-  const float2 pe = __fmul2_rn(p, make_float2(ex2_approx(q.x), ex2_approx(q.y)));
-  const float2 ha = __fmul2_rn(a, make_float2(0.5f, 0.5f)), nha = __fmul2_rn(a, make_float2(-0.5f, -0.5f));
-  const float2 s = __ffma2_rn(nha, pe, ha);  // 0.5 a E(z)
-  return __ffma2_rn(v, make_float2(0.5f, 0.5f), s);
+  const float2 n = make_float2(-fabsf(v.x), -fabsf(v.y));
+  const float2 r = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+  float2 q = __ffma2_rn(make_float2(4.712853462e-4f, 4.712853462e-4f), n, make_float2(7.064215249e-3f, 7.064215249e-3f));
+  q = __ffma2_rn(q, n, make_float2(5.175841926e-2f, 5.175841926e-2f));
+  q = __ffma2_rn(q, n, make_float2(-4.600918231e-1f, -4.600918231e-1f));
+  q = __ffma2_rn(q, n, make_float2(1.150727814f, 1.150727814f));
+  q = __ffma2_rn(q, n, make_float2(-1.000049354f, -1.000049354f));
+  const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+  return __ffma2_rn(n, e, r);
 }
 
-// CONV = false: BEATs epilogue (bias, GELU, raw store, fp32 residual * alpha).  CONV = true: folded-BatchNorm epilogue of
-// a 1x1 convolution in NHWC (raw pre-BN store, per-channel scale + shift, SiLU, bf16 residual); K and N need only be
-// multiples of 8: the TMA maps zero-fill the out-of-range part of the last K block / N tile.
-template <bool CONV>
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+  using C = Cfg<PAIR>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors
-  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS, not generic LD/ST)
+  // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors.  The offset is the
+  // same in both CTAs of a pair (same kernel, same dynamic-smem base), which the pair MMA and multicast commits rely on.
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
-  float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  float* stg_base = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
+  uint64_t* full_bar = bars;                      // [STAGES]  (pair: only the leader's are waited on)
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]       (pair: the leader's collect both CTAs' epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [BM] (mean, rstd), fused LN
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blocks = (g.M + BM - 1) / BM, n_blocks = (g.N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks, num_kb = (g.K + BK - 1) / BK;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int num_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int m_units = (g.M + C::UM - 1) / C::UM, n_blocks = (g.N + BN - 1) / BN;
+  const int num_tiles = m_units * n_blocks, num_kb = (g.K + BK - 1) / BK;
+  const bool ln = MODE == MODE_RES && g.ln_gamma != nullptr;
+  // iteration -> tile of this scheduling unit: tiles round-robin over units, n fastest, so the units working on the n tiles
+  // of one row block run side by side (they share the A rows in L2 and, with the fused LayerNorm, exchange row statistics)
+  auto tile_of = [&](int it, int& mu, int& nb) -> bool {
+    const int t = unit + it * num_units;
+    mu = t / n_blocks;
+    nb = t % n_blocks;
+    return t < num_tiles;
+  };
 
-  if (warp == 0 && lane == 0) {
+  if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
     for (int i = 0; i < STAGES; ++i) {
@@ -107,238 +156,476 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], EPI_WARPS);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[i], EPI_WARPS * (PAIR ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
+  __syncwarp();
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(tmem_slot, 512);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-        for (int kb = 0; kb < num_kb; ++kb) {
+  if (warp < CTRL_WARPS) {
+    ptx::setmaxnreg_dec<CTRL_REGS>();
+    if (warp == 0) {
+      // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
+      if (lane == 0) {
+        const uint32_t full0 = PAIR ? ptx::mapa(ptx::smem_u32(&full_bar[0]), 0) : 0u;  // the leader's full barriers
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0;; ++it) {
+          int mu, nb;
+          if (!tile_of(it, mu, nb)) break;
+          const int m0 = mu * C::UM + static_cast<int>(rank) * BM;
+          const int n0 = nb * BN + static_cast<int>(rank) * C::B_ROWS;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
+            if (PAIR) {
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
+              ptx::tma_load_2d_pair(sa, &map_a, full0 + stage * 8, kb * BK, m0);
+              ptx::tma_load_2d_pair(sa + C::A_BYTES, &map_b, full0 + stage * 8, kb * BK, n0);
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
+              ptx::tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m0);
+              ptx::tma_load_2d(sa + C::A_BYTES, &map_b, &full_bar[stage], kb * BK, n0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        // tail: every fill has been consumed and its release has landed here (no commit may target an exited CTA)
+        for (int s = 0; s < STAGES; ++s) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          unsigned char* sa = stage_base + stage * STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          ptx::tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
-          ptx::tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+    } else if (warp == 1 && (!PAIR || rank == 0)) {
+      // ===================== MMA issuer (leader CTA of a pair) =====================
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(C::UM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int it = 0;; ++it) {
+        int mu, nb;
+        if (!tile_of(it, mu, nb)) break;
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = ptx::smem_u32(stage_base + stage * STAGE_BYTES);
-          const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sa + A_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
+            const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sa + C::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-            ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          ptx::umma_commit(&empty_bar[stage]);                   // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);  // accumulator complete
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // Two warps per TMEM lane quarter; each owns four of the tile's eight 32-column chunks.  The fp32 residual of
-    // the NEXT chunk is prefetched into registers (8 independent 16-byte loads per lane) before the current chunk
-    // is processed, so HBM latency is overlapped instead of serialised behind the accumulator read.
-    const int ew = warp - 2, quarter = warp & 3, half = ew >> 2;
-    float* stg = stg_base + ew * (32 * 32);
-    const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
-    const bool has_res = !CONV && g.residual != nullptr;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float4 res_next[8];
-    auto load_res = [&](int tile, int c, float4 (&dst)[8]) {
-      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-      const int cc = n_blk * BN + c * 32 + csub * 4;
-      const int row0 = m_blk * BM + quarter * 32;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int grow = row0 + it * 4 + rsub;
-        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_res && tile < num_tiles && grow < g.M && cc < g.N)
-          dst[it] = __ldg(reinterpret_cast<const float4*>(g.residual + (size_t)grow * g.N + cc));
-      }
-    };
-    if (has_res) load_res(blockIdx.x, half * 4, res_next);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      const int row0 = m_blk * BM + quarter * 32;
-#pragma unroll 1
-      for (int ci = 0; ci < 4; ++ci) {
-        const int c = half * 4 + ci;
-        const int col0 = n_blk * BN + c * 32;
-        float4 res_cur[8];
-#pragma unroll
-        for (int it = 0; it < 8; ++it) res_cur[it] = res_next[it];
-        if (has_res) {
-          if (ci < 3) load_res(tile, c + 1, res_next);
-          else load_res(tile + gridDim.x, half * 4, res_next);
-        }
-        if (col0 < g.N) {  // warp-uniform
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(t_addr + c * 32, r);
-          ptx::tmem_ld_wait();
-          // lane owns one row: park its 32 columns (XOR-swizzled 16-byte slots), re-read so 8 lanes cover a 128 B row segment
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-          __syncwarp();
-          const int cc = col0 + csub * 4;
-          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
-          if (CONV && g.scale != nullptr && cc < g.N) scale4 = __ldg(reinterpret_cast<const float4*>(g.scale + cc));
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;
-            const int grow = row0 + rr;
-            if (grow < g.M && cc < g.N) {
-              float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((csub ^ (rr & 7)) << 2));
-              const size_t off = (size_t)grow * g.N + cc;
-              if (CONV) {
-                if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;  // pre-BN conv output (hook)
-                v.x = fmaf(v.x, scale4.x, bias4.x); v.y = fmaf(v.y, scale4.y, bias4.y);
-                v.z = fmaf(v.z, scale4.z, bias4.z); v.w = fmaf(v.w, scale4.w, bias4.w);
-                if (g.silu) {
-                  v.x *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.x));
-                  v.y *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.y));
-                  v.z *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.z));
-                  v.w *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.w));
-                }
-                if (g.res_bf16 != nullptr) {
-                  const uint2 rb = __ldg(reinterpret_cast<const uint2*>(g.res_bf16 + off));
-                  const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.x));
-                  const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.y));
-                  v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
-                }
-              } else {
-                v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-                if (g.gelu) {
-                  const float2 g0 = gelu_fast2(make_float2(v.x, v.y)), g1 = gelu_fast2(make_float2(v.z, v.w));
-                  v = make_float4(g0.x, g0.y, g1.x, g1.y);
-                }
-                if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
-                if (has_res) {
-                  v.x = fmaf(g.res_scale, res_cur[it].x, v.x); v.y = fmaf(g.res_scale, res_cur[it].y, v.y);
-                  v.z = fmaf(g.res_scale, res_cur[it].z, v.z); v.w = fmaf(g.res_scale, res_cur[it].w, v.w);
-                }
-              }
-              if (g.out != nullptr) {
-                const size_t oo = (size_t)grow * g.ldo + cc;
-                if (g.out_bf16) {
-                  uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + oo) = pk;
-                } else {
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + oo) = v;
-                }
-              }
+            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+              if (PAIR) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            if (PAIR) {
+              ptx::umma_commit_pair(&empty_bar[stage], 3);                      // both CTAs' smem slots are free
+              if (kb == num_kb - 1) ptx::umma_commit_pair(&tfull_bar[acc], 3);  // both halves of the accumulator complete
+            } else {
+              ptx::umma_commit(&empty_bar[stage]);
+              if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);
             }
           }
           __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 4..11) =====================
+    // Two warps per TMEM lane quarter; each owns four of the tile's eight 32-column chunks.  The TMEM load and the fp32
+    // residual of the NEXT chunk are in flight while the current chunk is processed.
+    ptx::setmaxnreg_inc<EPI_REGS>();
+    const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;
+    float* stg = stg_base + ew * (32 * 32);
+    const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
+    const bool has_res = MODE == MODE_RES && g.residual != nullptr;
+    float* ln_tile = ln ? g.ln_tiles + static_cast<size_t>(blockIdx.x) * BM * BN : nullptr;
+    const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    // the pre-LN tile is written, exchanged on and re-read within microseconds: keep it in L2 while the operands stream by
+    const uint64_t keep = ln ? ptx::policy_evict_last() : 0ull;
+    float ls[8], lq[8];  // fused LN: this lane's partial (sum, sum of squares) of rows i*4+rsub over the warp's 128 columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    auto load_res = [&](bool valid, int mu, int nb, int c, float4 (&dst)[8]) {
+      if (MODE != MODE_RES) return;
+      const int cc = nb * BN + c * 32 + csub * 4;
+      const int row0 = mu * C::UM + static_cast<int>(rank) * BM + quarter * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int grow = row0 + i * 4 + rsub;
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res && valid && grow < g.M && cc < g.N)
+          dst[i] = __ldcs(reinterpret_cast<const float4*>(g.residual + (size_t)grow * g.N + cc));  // read once; may be rewritten by this CTA's LayerNorm
+      }
+    };
+
+    auto process = [&](const uint32_t (&r)[32], const float4 (&res)[8], int mu, int nb, int c) {
+      const int col0 = nb * BN + c * 32;
+      if (col0 >= g.N) return;  // warp-uniform
+      const int lrow0 = quarter * 32, row0 = mu * C::UM + static_cast<int>(rank) * BM + lrow0;
+      // lane owns one row: park its 32 columns (XOR-swizzled 16-byte slots), re-read so 8 lanes cover a 128 B row segment
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+      __syncwarp();
+      const int cc = col0 + csub * 4;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+      if (MODE == MODE_CONV && g.scale != nullptr && cc < g.N) scale4 = __ldg(reinterpret_cast<const float4*>(g.scale + cc));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        const int grow = row0 + rr;
+        if (grow < g.M && cc < g.N) {
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((csub ^ (rr & 7)) << 2));
+          const size_t off = (size_t)grow * g.N + cc;
+          if (MODE == MODE_CONV) {
+            if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;  // pre-BN conv output (hook)
+            v.x = fmaf(v.x, scale4.x, bias4.x); v.y = fmaf(v.y, scale4.y, bias4.y);
+            v.z = fmaf(v.z, scale4.z, bias4.z); v.w = fmaf(v.w, scale4.w, bias4.w);
+            if (g.silu) {
+              v.x *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.x));
+              v.y *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.y));
+              v.z *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.z));
+              v.w *= rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v.w));
+            }
+            if (g.res_bf16 != nullptr) {
+              const uint2 rb = __ldg(reinterpret_cast<const uint2*>(g.res_bf16 + off));
+              const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.x));
+              const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.y));
+              v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
+            }
+          } else {
+            v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+            if (MODE == MODE_GELU) {
+              const float2 g0 = gelu_fast2(make_float2(v.x, v.y)), g1 = gelu_fast2(make_float2(v.z, v.w));
+              v = make_float4(g0.x, g0.y, g1.x, g1.y);
+            }
+            if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
+            if (MODE == MODE_RES) {
+              v.x = fmaf(g.res_scale, res[i].x, v.x); v.y = fmaf(g.res_scale, res[i].y, v.y);
+              v.z = fmaf(g.res_scale, res[i].z, v.z); v.w = fmaf(g.res_scale, res[i].w, v.w);
+            }
+          }
+          if (ln) {
+            ptx::st_global_hint(ln_tile + (lrow0 + rr) * BN + (c * 32 + csub * 4), v, keep);
+            ls[i] += (v.x + v.y) + (v.z + v.w);
+            lq[i] = fmaf(v.x, v.x, lq[i]); lq[i] = fmaf(v.y, v.y, lq[i]); lq[i] = fmaf(v.z, v.z, lq[i]); lq[i] = fmaf(v.w, v.w, lq[i]);
+          } else if (g.out != nullptr) {
+            const size_t oo = (size_t)grow * g.ldo + cc;
+            if (g.out_bf16) {
+              uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + oo) = pk;
+            } else {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + oo) = v;
+            }
+          }
         }
       }
-      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+      __syncwarp();
+    };
+
+    float4 res_a[8], res_b[8];
+    {
+      int mu, nb;
+      const bool v0 = tile_of(0, mu, nb);
+      load_res(v0, mu, nb, half * 4, res_a);
+    }
+    for (int it = 0;; ++it) {
+      int mu, nb;
+      if (!tile_of(it, mu, nb)) break;
+      int mu_n, nb_n;
+      const bool valid_n = tile_of(it + 1, mu_n, nb_n);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 128;
+      uint32_t ra[32], rb[32];
+      ptx::tmem_ld_32x32(t_addr, ra);
+      // chunk 0
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(t_addr + 32, rb);
+      load_res(true, mu, nb, half * 4 + 1, res_b);
+      process(ra, res_a, mu, nb, half * 4);
+      // chunk 1
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(t_addr + 64, ra);
+      load_res(true, mu, nb, half * 4 + 2, res_a);
+      process(rb, res_b, mu, nb, half * 4 + 1);
+      // chunk 2
+      ptx::tmem_ld_wait();
+      ptx::tmem_ld_32x32(t_addr + 96, rb);
+      load_res(true, mu, nb, half * 4 + 3, res_b);
+      process(ra, res_a, mu, nb, half * 4 + 2);
+      // chunk 3: every TMEM read of this accumulator has completed -> hand it back to the MMA warp before the last chunk
+      ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
+        else ptx::mbar_arrive(&tempty_bar[acc]);
+      }
+      load_res(valid_n, mu_n, nb_n, half * 4, res_a);
+      process(rb, res_b, mu, nb, half * 4 + 3);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      if (ln) {
+        // ---- fused LayerNorm (backbone.py:362,:373): the LN_NB CTAs holding the column tiles of these 128 rows swap
+        // per-row (sum, sum of squares) through L2, then each normalises its own tile; the tensor core is already busy
+        // with the next tiles (the accumulator was released above).  Requires all CTAs of the grid to be co-resident
+        // (grid <= #SMs, one CTA per SM): a CTA publishes its own statistics before it waits for its neighbours'.
+        const int m0 = mu * C::UM + static_cast<int>(rank) * BM, mb = m0 / BM;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            ls[i] += __shfl_xor_sync(0xffffffffu, ls[i], o);
+            lq[i] += __shfl_xor_sync(0xffffffffu, lq[i], o);
+          }
+        }
+        if (csub == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = m0 + quarter * 32 + i * 4 + rsub;
+            if (grow < g.M) g.ln_stats[(size_t)grow * (2 * LN_NB) + nb * 2 + half] = make_float2(ls[i], lq[i]);
+          }
+        }
+        __threadfence();                        // statistics (and the tile) are visible device-wide before the arrival below
+        ptx::named_bar_sync(1, EPI_THREADS);
+        const int nrows_blk = 2 * ((g.M + 2 * BM - 1) / (2 * BM));  // counters per 128-row block, pair-padded (host: ln_scratch_layout)
+        if (ew == 0 && lane == 0) {
+          red_release_gpu_add(&g.ln_count[mb], 1);
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(&g.ln_count[mb]) < LN_NB) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();  // a missing neighbour fails the launch instead of hanging the GPU
+          }
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);
+        const int t = ew * 32 + lane;
+        if (t < BM) {
+          float sum = 0.f, sq = 0.f;
+          if (m0 + t < g.M) {
+            const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + (size_t)(m0 + t) * (2 * LN_NB));
+#pragma unroll
+            for (int i = 0; i < LN_NB; ++i) {
+              const float4 p = __ldcg(sp + i);  // two (sum, sq) pairs; written by other SMs: read at L2
+              sum += p.x + p.z;
+              sq += p.y + p.w;
+            }
+          }
+          const float mean = sum * (1.0f / LN_C);
+          const float var = fmaxf(sq * (1.0f / LN_C) - mean * mean, 0.f);
+          rowstat[t] = make_float2(mean, rsqrtf(var + g.ln_eps));
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);
+        if (ew == 0 && lane == 0) {
+          // the last of the LN_NB CTAs to get here re-arms the counters for the next launch
+          if (atomicAdd(&g.ln_count[nrows_blk + mb], 1) == LN_NB - 1) {
+            g.ln_count[mb] = 0;
+            g.ln_count[nrows_blk + mb] = 0;
+          }
+        }
+        // normalise this CTA's 128 x 256 tile: a warp per row, 64 float4 per row = 2 per lane, R rows in flight
+        const int colq = nb * (BN / 4);  // first float4 column of the tile in a row of LN_C / 4
+        float4 ga[2], be[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          ga[i] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + colq + lane + 32 * i);
+          be[i] = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + colq + lane + 32 * i);
+        }
+        constexpr int R = 4;
+        const float4* tile4 = reinterpret_cast<const float4*>(ln_tile);
+#pragma unroll 1
+        for (int rp = 0; rp < BM / EPI_WARPS; rp += R) {
+          float4 v[R][2];
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int r = ew + EPI_WARPS * (rp + j);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) v[j][i] = ptx::ld_global_hint(tile4 + r * (BN / 4) + lane + 32 * i, keep);
+          }
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int r = ew + EPI_WARPS * (rp + j);
+            const float2 st = rowstat[r];
+            if (m0 + r < g.M) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                float4 y;
+                y.x = fmaf((v[j][i].x - st.x) * st.y, ga[i].x, be[i].x); y.y = fmaf((v[j][i].y - st.x) * st.y, ga[i].y, be[i].y);
+                y.z = fmaf((v[j][i].z - st.x) * st.y, ga[i].z, be[i].z); y.w = fmaf((v[j][i].w - st.x) * st.y, ga[i].w, be[i].w);
+                const size_t o = (size_t)(m0 + r) * (LN_C / 4) + colq + lane + 32 * i;
+                if (g.ln_out_f32) __stcs(reinterpret_cast<float4*>(g.ln_out_f32) + o, y);
+                if (g.ln_out_bf16) __stcs(reinterpret_cast<uint2*>(g.ln_out_bf16) + o, make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w)));
+              }
+            }
+          }
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);  // tile scratch and rowstat may be overwritten by the next tile
+      }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
   }
+}
+
+// CTA pairs (cta_group::2) by default; AVEXK_GEMM_PAIR=0 or avexk_gemm_config(0) selects the single-CTA kernel.
+int g_pair = -1;
+bool use_pair() {
+  if (g_pair < 0) {
+    const char* e = getenv("AVEXK_GEMM_PAIR");
+    g_pair = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pair != 0;
+}
+
+template <int MODE, bool PAIR>
+int launch_mode(const void* A, long long lda, const void* W, long long ldw, const GemmArgs& g, cudaStream_t st) {
+  using C = Cfg<PAIR>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ma, mb;
+  int rc = make_tmap_2d_bf16(&ma, A, g.M, g.K, lda, BM, BK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&mb, W, g.N, g.K, ldw, C::B_ROWS, BK);
+  if (rc) return rc;
+  const int m_units = ceil_div(g.M, C::UM), n_blocks = ceil_div(g.N, BN);
+  const int work = m_units * n_blocks;
+  const int max_units = PAIR ? num_sms() / 2 : num_sms();
+  const int units = work < max_units ? work : max_units;
+  prof_begin(st, KID_GEMM, 2.0 * g.M * g.N * g.K);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * units);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR>, ma, mb, g));
+  } else {
+    gemm_bf16_kernel<MODE, PAIR><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, g);
+  }
+  prof_end(st);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+template <int MODE>
+int launch_any(const void* A, long long lda, const void* W, long long ldw, const GemmArgs& g, cudaStream_t st) {
+  return use_pair() ? launch_mode<MODE, true>(A, lda, W, ldw, g, st) : launch_mode<MODE, false>(A, lda, W, ldw, g, st);
 }
 
 }  // namespace
 
-int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, int gelu,
+int gemm_bf16_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias, int gelu,
                      float* raw_out, const float* residual, float res_scale, void* out, long long ldo, int out_bf16,
                      cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.raw_out = raw_out; g.residual = residual; g.res_scale = res_scale;
+  g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16;
+  if (gelu) {
+    AVEXK_CHECK_ARG(residual == nullptr, "gemm: GELU and residual epilogues are exclusive");
+    return launch_any<MODE_GELU>(A, lda, W, ldw, g, st);
   }
-  GemmArgs g{M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16, nullptr, 0, nullptr};
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  prof_begin(st, KID_GEMM, 2.0 * M * N * K);
-  gemm_bf16_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(map_a, map_b, g);
-  prof_end(st);
-  AVEXK_LAUNCH_CHECK();
-  return AVEXK_OK;
+  if (residual != nullptr) return launch_any<MODE_RES>(A, lda, W, ldw, g, st);
+  return launch_any<MODE_PLAIN>(A, lda, W, ldw, g, st);
 }
 
-int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long long lda, const void* W, long long ldw, int M,
-                   int N, int K);
+// scratch of the fused LayerNorm epilogue: [pre-LN tile per CTA][row statistics][arrival / departure counters]
+struct LnScratch {
+  size_t tiles, stats, count, total;
+};
+LnScratch ln_scratch_layout(int M) {
+  const size_t blocks = 2 * (size_t)ceil_div(M, 2 * BM);  // 128-row blocks, padded to whole CTA pairs
+  const size_t ctas = blocks * LN_NB < (size_t)num_sms() ? blocks * LN_NB + 1 : (size_t)num_sms();  // +1: pair grids are even
+  LnScratch L;
+  L.tiles = 0;
+  L.stats = ctas * BM * BN * sizeof(float);
+  L.count = L.stats + blocks * BM * 2 * LN_NB * sizeof(float2);
+  L.total = L.count + ((2 * blocks * sizeof(int) + 255) & ~size_t(255));
+  return L;
+}
+size_t gemm_ln_scratch_bytes(int M) { return ln_scratch_layout(M).total; }
 
-// 1x1 convolution in NHWC: out[M, N] = act((A[M, K] @ W[N, K]^T) * scale + shift) (+ res); K, N multiples of 8.
+// y = LayerNorm(A @ W^T + bias + res_scale * residual) in one launch (N must be 768).  raw_out (optional) receives
+// A @ W^T + bias (the fc2 hook); ln_out_f32 may alias `residual` (a CTA reads a residual element before it rewrites it).
+// zero_counters: the counters at the end of `scratch` must be zero on entry; every launch leaves them zero, so only the
+// first use of a scratch buffer needs the memset.
+int gemm_bf16_ln_launch(const void* A, long long lda, const void* W, long long ldw, int M, int K, const float* bias, float* raw_out,
+                        const float* residual, float res_scale, const float* gamma, const float* beta, float eps,
+                        float* ln_out_f32, __nv_bfloat16* ln_out_bf16, void* scratch, size_t scratch_bytes, int zero_counters,
+                        cudaStream_t st) {
+  const LnScratch L = ln_scratch_layout(M);
+  AVEXK_CHECK_ARG(scratch != nullptr && scratch_bytes >= L.total && (reinterpret_cast<uintptr_t>(scratch) & 255) == 0,
+                  "gemm+LN: scratch too small or misaligned");
+  char* base = reinterpret_cast<char*>(scratch);
+  if (zero_counters) AVEXK_CUDA(cudaMemsetAsync(base + L.count, 0, L.total - L.count, st));
+  GemmArgs g{};
+  g.M = M; g.N = LN_C; g.K = K;
+  g.bias = bias; g.raw_out = raw_out; g.residual = residual; g.res_scale = res_scale;
+  g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_out_f32 = ln_out_f32; g.ln_out_bf16 = ln_out_bf16;
+  g.ln_tiles = reinterpret_cast<float*>(base + L.tiles);
+  g.ln_stats = reinterpret_cast<float2*>(base + L.stats);
+  g.ln_count = reinterpret_cast<int*>(base + L.count);
+  return launch_any<MODE_RES>(A, lda, W, ldw, g, st);
+}
+
+// 1x1 convolution in NHWC: out[M, N] = act((A[M, K] @ W[N, K]^T) * scale + shift) (+ res); K, N multiples of 8: the TMA
+// maps zero-fill the out-of-range part of the last K block / N tile.
 int conv1x1_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
                    const __nv_bfloat16* res, float* raw_out, void* out, int out_bf16, cudaStream_t st) {
   AVEXK_CHECK_ARG(K % 8 == 0 && N % 8 == 0 && K > 0 && N > 0, "conv1x1: channel counts must be multiples of 8 (K=%d N=%d)", K, N);
   if (M == 0) return AVEXK_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
-  CUtensorMap ma, mb;
-  int rc = gemm_make_maps(&ma, &mb, A, K, W, K, M, N, K);
-  if (rc) return rc;
-  GemmArgs g{M, N, K, shift, 0, raw_out, nullptr, 0.f, out, N, out_bf16, scale, silu, res};
-  const int tiles = ceil_div(M, BM) * ceil_div(N, BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  prof_begin(st, KID_GEMM, 2.0 * M * N * K);
-  gemm_bf16_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(ma, mb, g);
-  prof_end(st);
-  AVEXK_LAUNCH_CHECK();
-  return AVEXK_OK;
-}
-
-int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long long lda, const void* W, long long ldw, int M,
-                   int N, int K) {
-  int rc = make_tmap_2d_bf16(map_a, A, M, K, lda, BM, BK);
-  if (rc) return rc;
-  return make_tmap_2d_bf16(map_b, W, N, K, ldw, BN, BK);
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = shift; g.raw_out = raw_out; g.out = out; g.ldo = N; g.out_bf16 = out_bf16;
+  g.scale = scale; g.silu = silu; g.res_bf16 = res;
+  return launch_any<MODE_CONV>(A, K, W, K, g, st);
 }
 
 }  // namespace avexk
+
+extern "C" int avexk_gemm_config(int pair) {
+  const int prev = avexk::use_pair() ? 1 : 0;
+  if (pair == 0 || pair == 1) avexk::g_pair = pair;
+  return prev;
+}
 
 extern "C" int avexk_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                                const float* bias, int gelu, float* raw_out, const float* residual, float res_scale, void* out,
@@ -349,9 +636,22 @@ extern "C" int avexk_gemm_bf16(const void* A, long long lda, const void* W, long
   AVEXK_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0 && (out == nullptr || (ldo >= N && ldo % 8 == 0)),
                   "avexk_gemm_bf16: bad leading dimensions");
   if (M == 0) return AVEXK_OK;
-  CUtensorMap ma, mb;
-  int rc = gemm_make_maps(&ma, &mb, A, lda, W, ldw, M, N, K);
-  if (rc) return rc;
-  return gemm_bf16_launch(ma, mb, M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16,
+  return gemm_bf16_launch(A, lda, W, ldw, M, N, K, bias, gelu, raw_out, residual, res_scale, out, ldo, out_bf16,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t avexk_gemm_ln_scratch_bytes(int M) { return M > 0 ? avexk::gemm_ln_scratch_bytes(M) : 0; }
+
+extern "C" int avexk_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
+                                  float* raw_out, const float* residual, float res_scale, const float* gamma, const float* beta,
+                                  float eps, float* out_f32, void* out_bf16, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(A && W && gamma && beta && (out_f32 || out_bf16), "avexk_gemm_bf16_ln: null operand");
+  AVEXK_CHECK_ARG(N == LN_C, "avexk_gemm_bf16_ln: the fused LayerNorm epilogue is built for N = %d (got %d)", LN_C, N);
+  AVEXK_CHECK_ARG(M >= 0 && K > 0 && K % 8 == 0 && lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0,
+                  "avexk_gemm_bf16_ln: unsupported shape / leading dimensions");
+  if (M == 0) return AVEXK_OK;
+  return gemm_bf16_ln_launch(A, lda, W, ldw, M, K, bias, raw_out, residual, res_scale, gamma, beta, eps, out_f32,
+                             reinterpret_cast<__nv_bfloat16*>(out_bf16), scratch, scratch_bytes, 1,
+                             reinterpret_cast<cudaStream_t>(stream));
 }

@@ -7,11 +7,14 @@
 namespace avexk {
 
 // gemm_tc.cu
-int gemm_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, const void* A, long long lda, const void* W, long long ldw, int M,
-                   int N, int K);
-int gemm_bf16_launch(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, int gelu,
+int gemm_bf16_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias, int gelu,
                      float* raw_out, const float* residual, float res_scale, void* out, long long ldo, int out_bf16,
                      cudaStream_t st);
+size_t gemm_ln_scratch_bytes(int M);
+int gemm_bf16_ln_launch(const void* A, long long lda, const void* W, long long ldw, int M, int K, const float* bias, float* raw_out,
+                        const float* residual, float res_scale, const float* gamma, const float* beta, float eps,
+                        float* ln_out_f32, __nv_bfloat16* ln_out_bf16, void* scratch, size_t scratch_bytes, int zero_counters,
+                        cudaStream_t st);
 int conv1x1_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
                    const __nv_bfloat16* res, float* raw_out, void* out, int out_bf16, cudaStream_t st);
 // elementwise.cu

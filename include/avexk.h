@@ -87,6 +87,19 @@ int avexk_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, 
                     int gelu, float* raw_out, const float* residual, float res_scale, void* out, long long ldo,
                     int out_bf16, void* stream);
 
+/* The same GEMM with the post-LN block tail fused (backbone.py:360-362, :372-373), N == 768 only:
+ *   v = A @ W^T + bias;  raw_out = v (optional hook);  y = LayerNorm(v + res_scale * residual) * gamma + beta
+ * y is written as fp32 (out_f32, may alias `residual`) and / or bf16 (out_bf16).  `scratch` holds the pre-LN sums of the
+ * row blocks in flight (avexk_gemm_ln_scratch_bytes(M) bytes, stays L2-resident); nothing of size [M,768] fp32 other than
+ * the residual read and the y write touches HBM. */
+size_t avexk_gemm_ln_scratch_bytes(int M);
+int avexk_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
+                       float* raw_out, const float* residual, float res_scale, const float* gamma, const float* beta, float eps,
+                       float* out_f32, void* out_bf16, void* scratch, size_t scratch_bytes, void* stream);
+/* Tuning knob: 1 (default) = CTA pairs (tcgen05 cta_group::2, 256x256 tiles), 0 = single-CTA 128x256 tiles.  Returns the
+ * previous setting; any other argument only queries.  Environment override at first use: AVEXK_GEMM_PAIR=0. */
+int avexk_gemm_config(int pair);
+
 /* Row LayerNorm over the last dimension C (eps 1e-5): y = (x - mu) / sqrt(var + eps) * gamma + beta.
  * x [M,C] fp32; writes out_f32 and / or out_bf16 (either may be NULL). */
 int avexk_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, float* out_f32,

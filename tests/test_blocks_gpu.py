@@ -34,8 +34,16 @@ GEMM_SHAPES = [
 ]  # fmt: skip
 
 
+@pytest.fixture(params=[1, 0], ids=["cta_pair", "single_cta"])
+def pair(request, lib):
+    """Both GEMM kernels: CTA pairs (tcgen05 cta_group::2, the default) and single-CTA tiles."""
+    prev = lib.avexk_gemm_config(request.param)
+    yield request.param
+    lib.avexk_gemm_config(prev)
+
+
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_plain_fp32_out(lib, M, N, K):
+def test_gemm_plain_fp32_out(lib, pair, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
@@ -49,7 +57,7 @@ def test_gemm_plain_fp32_out(lib, M, N, K):
     assert err <= 2e-3, f"max abs err {err}"
 
 
-def test_gemm_epilogues(lib):
+def test_gemm_epilogues(lib, pair):
     M, N, K = 777, 768, 768
     g = torch.Generator(device="cuda").manual_seed(5)
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
@@ -75,6 +83,44 @@ def test_gemm_epilogues(lib):
     _check(lib.avexk_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, None, 0, None, None, 0.0,
                                outb.data_ptr(), N, 1, _stream()), lib)  # fmt: skip
     assert ((outb.float() - (ref - bias)).abs() <= 8e-3 * (ref - bias).abs() + 2e-3).all()
+
+
+@pytest.mark.parametrize("M,K,raw,inplace", [(1, 768, False, False), (100, 768, True, False), (129, 3072, False, True),
+                                              (1000, 768, True, True), (40000, 768, False, True), (38017, 3072, True, False)])
+def test_gemm_fused_layernorm(lib, pair, M, K, raw, inplace):
+    """out_proj / fc2 tail in one launch: LN(A W^T + b + alpha * residual), optional raw (hook) store, in-place residual."""
+    N, alpha = 768, 2.2133638
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g) + 0.3
+    gamma = torch.randn(N, device="cuda", generator=g)
+    beta = torch.randn(N, device="cuda", generator=g)
+    lin = A.float() @ W.float().T + bias
+    ref = torch.nn.functional.layer_norm(lin + alpha * res, (N,), gamma, beta, 1e-5)
+    nbytes = lib.avexk_gemm_ln_scratch_bytes(M)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    res_buf = res.clone()
+    o32 = res_buf if inplace else torch.full((M, N), float("nan"), device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    rawt = torch.full((M, N), float("nan"), device="cuda") if raw else None
+    for _ in range(1 if inplace else 2):  # second pass over a dirty scratch
+        _check(lib.avexk_gemm_bf16_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), rawt.data_ptr() if raw else None,
+                                      res_buf.data_ptr(), alpha, gamma.data_ptr(), beta.data_ptr(), 1e-5, o32.data_ptr(), o16.data_ptr(),
+                                      scratch.data_ptr(), nbytes, _stream()), lib)  # fmt: skip
+    assert torch.isfinite(o32).all()
+    assert (o32 - ref).abs().max().item() <= 3e-3
+    assert torch.equal(o16, o32.to(torch.bfloat16))
+    if raw:
+        assert (rawt - lin).abs().max().item() <= 2e-3
+    # bf16-only output (the last layer keeps no fp32 copy when only xb is wanted) and scratch-size check
+    o16b = torch.empty_like(o16)
+    _check(lib.avexk_gemm_bf16_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), None, res.data_ptr(), alpha,
+                                  gamma.data_ptr(), beta.data_ptr(), 1e-5, None, o16b.data_ptr(), scratch.data_ptr(), nbytes, _stream()), lib)  # fmt: skip
+    assert torch.equal(o16b, o16)
+    assert lib.avexk_gemm_bf16_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), None, res.data_ptr(), alpha, gamma.data_ptr(),
+                                  beta.data_ptr(), 1e-5, None, o16b.data_ptr(), scratch.data_ptr(), 16, _stream()) != 0  # fmt: skip
 
 
 def test_gemm_rejects_bad_shapes(lib):
