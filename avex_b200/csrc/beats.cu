@@ -8,6 +8,8 @@
 //   att  bf16 [M,C]   attention output, token-major (the reference's permute+contiguous never happens)
 //   h    bf16 [M,4C]  GELU(fc1)
 //   tmp  fp32 [M,C]   pre-LayerNorm sums (GEMM epilogue output)
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -229,11 +231,14 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
     return gemm_bf16_launch(A, K, W, K, (int)M, Nn, K, bias, gelu, raw, res, rs, o, Nn, obf, st);
   };
   // GEMM + DeepNorm residual + LayerNorm in one launch when the width matches the fused epilogue (BEATs-base: 768)
-  const bool fuse_ln = C == 768;
+  // AVEXK_FUSE_LN: 0 = separate LayerNorm launches, 1 (default) = fc2 only, 2 = out_proj and fc2.  Measured at config #2:
+  // 35.9 / 35.2 / 35.4 ms per step: the K=768 out_proj tile is too short to hide the statistics exchange.
+  static const int fuse_level = [] { const char* e = getenv("AVEXK_FUSE_LN"); return e ? atoi(e) : 1; }();
+  const bool fuse_ln = C == 768 && fuse_level > 0;
   int ln_first = 1;  // the scratch counters are zeroed once per forward; every launch leaves them zero
   auto gemm_ln = [&](const void* A, int K, const __nv_bfloat16* W, const float* bias, float* raw, const float* gamma, const float* beta,
                      float* dst_f32, __nv_bfloat16* dst_bf16) -> int {
-    if (fuse_ln) {
+    if (fuse_ln && (fuse_level >= 2 || K > C)) {
       const int zero = ln_first;
       ln_first = 0;
       return gemm_bf16_ln_launch(A, K, W, K, (int)M, K, bias, raw, x, alpha, gamma, beta, d.ln_eps, dst_f32, dst_bf16, ln_ws, ln_ws_bytes,

@@ -133,16 +133,19 @@ stem_kernel(const float* __restrict__ mel, const unsigned* __restrict__ minmax, 
 // depthwise k x k conv + BN + SiLU, NHWC bf16, with the squeeze-excitation sums
 // ---------------------------------------------------------------------------------------------------------
 constexpr int DW_PIX = 256;  // output pixels per CTA
+constexpr float SE_FIX = 16777216.0f;  // 2^24
 template <int K>
 __global__ void __launch_bounds__(256)
 dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho, int Wo, int stride,
               const float* __restrict__ wkk, const float* __restrict__ scale, const float* __restrict__ shift,
-              __nv_bfloat16* __restrict__ out, float* __restrict__ se_sum) {
-  extern __shared__ float sse[];  // [C]
+              __nv_bfloat16* __restrict__ out, unsigned long long* __restrict__ se_sum) {
+  // squeeze-excitation sums in 40.24 fixed point: integer adds are associative, so the atomics below give the same bits
+  // whatever order the pixel groups / CTAs arrive in (a float atomicAdd made results differ from run to run)
+  extern __shared__ unsigned long long sse[];  // [C]
   const int b = blockIdx.y, CV = C >> 3;
   const int PG = blockDim.x / CV;  // pixel groups in flight
   const int cv = threadIdx.x % CV, pg = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sse[i] = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sse[i] = 0ull;
   __syncthreads();
   constexpr int PAD = (K - 1) / 2;
   const int p_end = min(Ho * Wo, (int)(blockIdx.x + 1) * DW_PIX);
@@ -190,7 +193,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho,
     }
     if (se_sum != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&sse[cv * 8 + i], se[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(&sse[cv * 8 + i], static_cast<unsigned long long>(__float2ll_rn(se[i] * SE_FIX)));
     }
   }
   if (se_sum != nullptr) {
@@ -203,14 +206,15 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho,
 // squeeze-excitation MLP per clip: s = sigmoid(W2 silu(W1 avg + b1) + b2)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-se_mlp_kernel(const float* __restrict__ se_sum, float inv_hw, int C, int S, const float* __restrict__ w1,
+se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int C, int S, const float* __restrict__ w1,
               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
               float* __restrict__ se_scale) {
   extern __shared__ float sm[];  // avg[C], hid[S]
   float* avg = sm;
   float* hid = sm + C;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int c = tid; c < C; c += blockDim.x) avg[c] = se_sum[(size_t)b * C + c] * inv_hw;
+  for (int c = tid; c < C; c += blockDim.x)
+    avg[c] = static_cast<float>(static_cast<double>(static_cast<long long>(se_sum[(size_t)b * C + c])) * (1.0 / SE_FIX)) * inv_hw;
   __syncthreads();
   for (int j = warp; j < S; j += blockDim.x / 32) {
     float a = 0.f;
@@ -224,6 +228,12 @@ se_mlp_kernel(const float* __restrict__ se_sum, float inv_hw, int C, int S, cons
     for (int j = 0; j < S; ++j) a = fmaf(__ldg(w2 + (size_t)c * S + j), hid[j], a);
     se_scale[(size_t)b * C + c] = 1.0f / (1.0f + __expf(-a));
   }
+}
+
+__global__ void __launch_bounds__(256)
+se_fix_to_float_kernel(const unsigned long long* __restrict__ acc, long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(static_cast<double>(static_cast<long long>(acc[i])) * (1.0 / SE_FIX));
 }
 
 // x[b, p, c] *= s[b, c]   (bf16 NHWC, 8 channels per thread)
@@ -327,13 +337,13 @@ inline int conv_out(int n, int k, int stride) { return (n + 2 * ((k - 1) / 2) - 
 }  // namespace
 
 int launch_dwconv(const __nv_bfloat16* in, int B, int H, int W, int C, int k, int stride, const float* wkk, const float* scale,
-                  const float* shift, __nv_bfloat16* out, float* se_sum, cudaStream_t st) {
+                  const float* shift, __nv_bfloat16* out, unsigned long long* se_sum, cudaStream_t st) {
   AVEXK_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "dwconv: unsupported C=%d k=%d stride=%d", C, k, stride);
   if (B == 0) return AVEXK_OK;
   const int Ho = conv_out(H, k, stride), Wo = conv_out(W, k, stride);
   dim3 grid(ceil_div((long long)Ho * Wo, DW_PIX), B);
-  if (k == 3) dwconv_kernel<3><<<grid, 256, C * sizeof(float), st>>>(in, H, W, C, Ho, Wo, stride, wkk, scale, shift, out, se_sum);
-  else dwconv_kernel<5><<<grid, 256, C * sizeof(float), st>>>(in, H, W, C, Ho, Wo, stride, wkk, scale, shift, out, se_sum);
+  if (k == 3) dwconv_kernel<3><<<grid, 256, C * sizeof(unsigned long long), st>>>(in, H, W, C, Ho, Wo, stride, wkk, scale, shift, out, se_sum);
+  else dwconv_kernel<5><<<grid, 256, C * sizeof(unsigned long long), st>>>(in, H, W, C, Ho, Wo, stride, wkk, scale, shift, out, se_sum);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
 }
@@ -357,12 +367,18 @@ extern "C" int avexk_dwconv_nhwc(const void* in_bf16, int B, int H, int W, int C
   using namespace avexk;
   AVEXK_CHECK_ARG(in_bf16 && w_ckk && scale && shift && out_bf16 && workspace, "avexk_dwconv_nhwc: null argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  float* wkk = reinterpret_cast<float*>(workspace);  // >= C*k*k floats
+  // workspace: [B*C fixed-point accumulators (8 bytes each)][C*k*k repacked weights (fp32)]
+  unsigned long long* acc = reinterpret_cast<unsigned long long*>(workspace);
+  float* wkk = reinterpret_cast<float*>(acc + (size_t)B * C);
   dw_pack_kernel<<<ceil_div(C * k * k, 256), 256, 0, st>>>(w_ckk, C, k * k, wkk);
   AVEXK_LAUNCH_CHECK();
-  if (se_sum) AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(float) * (size_t)B * C, st));
-  return launch_dwconv(reinterpret_cast<const __nv_bfloat16*>(in_bf16), B, H, W, C, k, stride, wkk, scale, shift,
-                       reinterpret_cast<__nv_bfloat16*>(out_bf16), se_sum, st);
+  if (se_sum) AVEXK_CUDA(cudaMemsetAsync(acc, 0, sizeof(unsigned long long) * (size_t)B * C, st));
+  int rc = launch_dwconv(reinterpret_cast<const __nv_bfloat16*>(in_bf16), B, H, W, C, k, stride, wkk, scale, shift,
+                         reinterpret_cast<__nv_bfloat16*>(out_bf16), se_sum ? acc : nullptr, st);
+  if (rc || !se_sum || B == 0) return rc;
+  se_fix_to_float_kernel<<<ceil_div((long long)B * C, 256), 256, 0, st>>>(acc, (long long)B * C, se_sum);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
 }
 
 extern "C" int avexk_effnet_create(const avexk_effnet_block_cfg* blocks, int num_blocks, int stem_out, int head_out,
@@ -472,7 +488,7 @@ EffPlan effnet_plan(const avexk_effnet* h, int B, int H0, int W0) {
   p.exp = al(ex * B * 2);
   p.dw = al(dw * B * 2);
   p.raw = al(raw * B * 4);
-  p.se = al(se * B * 4);
+  p.se = al(se * B * 8);  // fixed-point SE accumulators (8 bytes); the fp32 SE scales use half of a region
   p.total = 2 * p.act + p.exp + p.dw + 2 * p.raw + 2 * p.se + al((size_t)B * h->head_out * 4) + 4096;
   return p;
 }
@@ -512,7 +528,7 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
   __nv_bfloat16* dw = reinterpret_cast<__nv_bfloat16*>(p); p += pl.dw;
   float* raw = reinterpret_cast<float*>(p); p += pl.raw;
   float* raw2 = reinterpret_cast<float*>(p); p += pl.raw;
-  float* se_sum = reinterpret_cast<float*>(p); p += pl.se;
+  unsigned long long* se_sum = reinterpret_cast<unsigned long long*>(p); p += pl.se;
   float* se_scale = reinterpret_cast<float*>(p); p += pl.se;
   float* pooled = reinterpret_cast<float*>(p);
   const int nb = (int)h->cfg.size();
@@ -543,7 +559,7 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
       dw_in = ex;
     }
     const int Ho = conv_out(H, c.kernel, c.stride), Wo = conv_out(W, c.kernel, c.stride);
-    AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(float) * (size_t)B * c.cexp, st));
+    AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(unsigned long long) * (size_t)B * c.cexp, st));
     TRY(launch_dwconv(dw_in, B, H, W, c.cexp, c.kernel, c.stride, b.dw_w, b.dw_scale, b.dw_shift, dw, se_sum, st));
     se_mlp_kernel<<<B, 256, (c.cexp + c.csq) * sizeof(float), st>>>(se_sum, 1.0f / (float)(Ho * Wo), c.cexp, c.csq, b.se1_w, b.se1_b,
                                                                     b.se2_w, b.se2_b, se_scale);

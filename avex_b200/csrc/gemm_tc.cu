@@ -37,6 +37,7 @@ constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
 constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;  // 32 rows x 32 fp32, XOR-swizzled (no padding)
 constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS);
 constexpr int CTRL_REGS = 64, EPI_REGS = 216;  // 128 * 64 + 256 * 216 = 63488 <= 65536
+constexpr bool LN_DEFER = false;  // normalise tile i after tile i+1 has been drained (measured slower: 0.44 vs 0.39 ms on out_proj)
 constexpr int LN_C = 768, LN_NB = LN_C / BN;   // the fused LayerNorm epilogue is built for rows of 3 tiles
 
 template <bool PAIR>
@@ -70,7 +71,7 @@ struct GemmArgs {
   float ln_eps;
   float* ln_out_f32;
   __nv_bfloat16* ln_out_bf16;
-  float* ln_tiles;   // [gridDim.x][128][256] fp32: this CTA's pre-LN tile, re-read from L2 a few microseconds later
+  float* ln_tiles;   // [gridDim.x][2][128][256] fp32: this CTA's last two pre-LN tiles, re-read from L2 microseconds later
   float2* ln_stats;  // [ceil(M/128)*128][2*LN_NB] (sum, sum of squares) over 128 columns of a row
   int* ln_count;     // [2][ceil(M/128)]: arrivals / departures per 128-row block; zero before and after every launch
 };
@@ -256,7 +257,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* stg = stg_base + ew * (32 * 32);
     const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
     const bool has_res = MODE == MODE_RES && g.residual != nullptr;
-    float* ln_tile = ln ? g.ln_tiles + static_cast<size_t>(blockIdx.x) * BM * BN : nullptr;
+    float* ln_tile = ln ? g.ln_tiles + static_cast<size_t>(blockIdx.x) * 2 * BM * BN : nullptr;  // two tiles: i is normalised after i+1 is drained
+    float* ln_cur = ln_tile;
     const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
     // the pre-LN tile is written, exchanged on and re-read within microseconds: keep it in L2 while the operands stream by
     const uint64_t keep = ln ? ptx::policy_evict_last() : 0ull;
@@ -277,7 +279,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     };
 
-    auto process = [&](const uint32_t (&r)[32], const float4 (&res)[8], int mu, int nb, int c) {
+    float4 bias_t[4], scale_t[4];  // this lane's bias (and BN scale) columns of the tile's four chunks, loaded ahead of the accumulator
+    auto process = [&](const uint32_t (&r)[32], const float4 (&res)[8], int mu, int nb, int c, const float4 bias4, const float4 scale4) {
       const int col0 = nb * BN + c * 32;
       if (col0 >= g.N) return;  // warp-uniform
       const int lrow0 = quarter * 32, row0 = mu * C::UM + static_cast<int>(rank) * BM + lrow0;
@@ -287,9 +290,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         *reinterpret_cast<uint4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
       __syncwarp();
       const int cc = col0 + csub * 4;
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), scale4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (g.bias != nullptr && cc < g.N) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
-      if (MODE == MODE_CONV && g.scale != nullptr && cc < g.N) scale4 = __ldg(reinterpret_cast<const float4*>(g.scale + cc));
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub;
@@ -326,7 +326,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
           if (ln) {
-            ptx::st_global_hint(ln_tile + (lrow0 + rr) * BN + (c * 32 + csub * 4), v, keep);
+            ptx::st_global_hint(ln_cur + (lrow0 + rr) * BN + (c * 32 + csub * 4), v, keep);
             ls[i] += (v.x + v.y) + (v.z + v.w);
             lq[i] = fmaf(v.x, v.x, lq[i]); lq[i] = fmaf(v.y, v.y, lq[i]); lq[i] = fmaf(v.z, v.z, lq[i]); lq[i] = fmaf(v.w, v.w, lq[i]);
           } else if (g.out != nullptr) {
@@ -343,7 +343,106 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
     };
 
+    // publish this warp's partial row statistics of the tile just drained and announce the tile (fused LN, pass 1 tail)
+    auto ln_publish = [&](int mu, int nb) {
+      const int m0 = mu * C::UM + static_cast<int>(rank) * BM, mb = m0 / BM;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          ls[i] += __shfl_xor_sync(0xffffffffu, ls[i], o);
+          lq[i] += __shfl_xor_sync(0xffffffffu, lq[i], o);
+        }
+      }
+      if (csub == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int grow = m0 + quarter * 32 + i * 4 + rsub;
+          if (grow < g.M) g.ln_stats[(size_t)grow * (2 * LN_NB) + nb * 2 + half] = make_float2(ls[i], lq[i]);
+        }
+      }
+      // CTA barrier + release at gpu scope by the announcing thread: the statistics written by the other warps are ordered
+      // before the arrival by cumulativity, so no per-thread __threadfence() (a full memory barrier per warp) is needed
+      ptx::named_bar_sync(1, EPI_THREADS);
+      if (ew == 0 && lane == 0) red_release_gpu_add(&g.ln_count[mb], 1);
+    };
+    // wait for the neighbours' statistics of tile (mu, nb), then normalise this CTA's copy of it (fused LN, pass 2)
+    auto ln_finish = [&](int mu, int nb, int buf) {
+      const int m0 = mu * C::UM + static_cast<int>(rank) * BM, mb = m0 / BM;
+      const int nrows_blk = 2 * ((g.M + 2 * BM - 1) / (2 * BM));  // counters per 128-row block, pair-padded (host: ln_scratch_layout)
+      if (ew == 0 && lane == 0) {
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(&g.ln_count[mb]) < LN_NB) {
+          __nanosleep(32);
+          if (++spins > (1u << 24)) __trap();  // a missing neighbour fails the launch instead of hanging the GPU
+        }
+      }
+      ptx::named_bar_sync(1, EPI_THREADS);
+      const int t = ew * 32 + lane;
+      if (t < BM) {
+        float sum = 0.f, sq = 0.f;
+        if (m0 + t < g.M) {
+          const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + (size_t)(m0 + t) * (2 * LN_NB));
+#pragma unroll
+          for (int i = 0; i < LN_NB; ++i) {
+            const float4 p = __ldcg(sp + i);  // two (sum, sq) pairs; written by other SMs: read at L2
+            sum += p.x + p.z;
+            sq += p.y + p.w;
+          }
+        }
+        const float mean = sum * (1.0f / LN_C);
+        const float var = fmaxf(sq * (1.0f / LN_C) - mean * mean, 0.f);
+        rowstat[t] = make_float2(mean, rsqrtf(var + g.ln_eps));
+      }
+      ptx::named_bar_sync(1, EPI_THREADS);
+      if (ew == 0 && lane == 0) {
+        // the last of the LN_NB CTAs to get here re-arms the counters for the next launch
+        if (atomicAdd(&g.ln_count[nrows_blk + mb], 1) == LN_NB - 1) {
+          g.ln_count[mb] = 0;
+          g.ln_count[nrows_blk + mb] = 0;
+        }
+      }
+      // normalise the 128 x 256 tile: a warp per row, 64 float4 per row = 2 per lane, R rows in flight
+      const int colq = nb * (BN / 4);  // first float4 column of the tile in a row of LN_C / 4
+      float4 ga[2], be[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        ga[i] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + colq + lane + 32 * i);
+        be[i] = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + colq + lane + 32 * i);
+      }
+      constexpr int R = 4;
+      const float4* tile4 = reinterpret_cast<const float4*>(ln_tile + (size_t)buf * BM * BN);
+#pragma unroll 1
+      for (int rp = 0; rp < BM / EPI_WARPS; rp += R) {
+        float4 v[R][2];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int r = ew + EPI_WARPS * (rp + j);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) v[j][i] = ptx::ld_global_hint(tile4 + r * (BN / 4) + lane + 32 * i, keep);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int r = ew + EPI_WARPS * (rp + j);
+          const float2 st = rowstat[r];
+          if (m0 + r < g.M) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              float4 y;
+              y.x = fmaf((v[j][i].x - st.x) * st.y, ga[i].x, be[i].x); y.y = fmaf((v[j][i].y - st.x) * st.y, ga[i].y, be[i].y);
+              y.z = fmaf((v[j][i].z - st.x) * st.y, ga[i].z, be[i].z); y.w = fmaf((v[j][i].w - st.x) * st.y, ga[i].w, be[i].w);
+              const size_t o = (size_t)(m0 + r) * (LN_C / 4) + colq + lane + 32 * i;
+              if (g.ln_out_f32) __stcs(reinterpret_cast<float4*>(g.ln_out_f32) + o, y);
+              if (g.ln_out_bf16) __stcs(reinterpret_cast<uint2*>(g.ln_out_bf16) + o, make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w)));
+            }
+          }
+        }
+      }
+      ptx::named_bar_sync(1, EPI_THREADS);  // rowstat and (two tiles on) this scratch buffer may be overwritten
+    };
+
     float4 res_a[8], res_b[8];
+    int mu_p = 0, nb_p = 0, it_last = -1;
     {
       int mu, nb;
       const bool v0 = tile_of(0, mu, nb);
@@ -356,6 +455,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool valid_n = tile_of(it + 1, mu_n, nb_n);
 #pragma unroll
       for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
+      if (ln) ln_cur = ln_tile + (size_t)(it & 1) * BM * BN;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int cc = nb * BN + (half * 4 + ci) * 32 + csub * 4;
+        bias_t[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+        scale_t[ci] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (g.bias != nullptr && cc < g.N) bias_t[ci] = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
+        if (MODE == MODE_CONV && g.scale != nullptr && cc < g.N) scale_t[ci] = __ldg(reinterpret_cast<const float4*>(g.scale + cc));
+      }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 128;
@@ -365,17 +473,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(t_addr + 32, rb);
       load_res(true, mu, nb, half * 4 + 1, res_b);
-      process(ra, res_a, mu, nb, half * 4);
+      process(ra, res_a, mu, nb, half * 4, bias_t[0], scale_t[0]);
       // chunk 1
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(t_addr + 64, ra);
       load_res(true, mu, nb, half * 4 + 2, res_a);
-      process(rb, res_b, mu, nb, half * 4 + 1);
+      process(rb, res_b, mu, nb, half * 4 + 1, bias_t[1], scale_t[1]);
       // chunk 2
       ptx::tmem_ld_wait();
       ptx::tmem_ld_32x32(t_addr + 96, rb);
       load_res(true, mu, nb, half * 4 + 3, res_b);
-      process(ra, res_a, mu, nb, half * 4 + 2);
+      process(ra, res_a, mu, nb, half * 4 + 2, bias_t[2], scale_t[2]);
       // chunk 3: every TMEM read of this accumulator has completed -> hand it back to the MMA warp before the last chunk
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
@@ -385,105 +493,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         else ptx::mbar_arrive(&tempty_bar[acc]);
       }
       load_res(valid_n, mu_n, nb_n, half * 4, res_a);
-      process(rb, res_b, mu, nb, half * 4 + 3);
+      process(rb, res_b, mu, nb, half * 4 + 3, bias_t[3], scale_t[3]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
       if (ln) {
         // ---- fused LayerNorm (backbone.py:362,:373): the LN_NB CTAs holding the column tiles of these 128 rows swap
-        // per-row (sum, sum of squares) through L2, then each normalises its own tile; the tensor core is already busy
-        // with the next tiles (the accumulator was released above).  Requires all CTAs of the grid to be co-resident
-        // (grid <= #SMs, one CTA per SM): a CTA publishes its own statistics before it waits for its neighbours'.
-        const int m0 = mu * C::UM + static_cast<int>(rank) * BM, mb = m0 / BM;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            ls[i] += __shfl_xor_sync(0xffffffffu, ls[i], o);
-            lq[i] += __shfl_xor_sync(0xffffffffu, lq[i], o);
-          }
+        // per-row (sum, sum of squares) through L2, then each normalises its own tile.  The tensor core is already busy
+        // with the next tiles (the accumulator was released above), and the normalisation of tile i is deferred until
+        // tile i+1 has been drained and published, so the wait for the neighbours is never exposed.  Requires all CTAs of
+        // the grid to be co-resident (grid <= #SMs, one CTA per SM): a CTA publishes before it waits.
+        ln_publish(mu, nb);
+        if (!LN_DEFER) {
+          ln_finish(mu, nb, it & 1);
+        } else {
+          if (it > 0) ln_finish(mu_p, nb_p, (it - 1) & 1);
+          mu_p = mu;
+          nb_p = nb;
+          it_last = it;
         }
-        if (csub == 0) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int grow = m0 + quarter * 32 + i * 4 + rsub;
-            if (grow < g.M) g.ln_stats[(size_t)grow * (2 * LN_NB) + nb * 2 + half] = make_float2(ls[i], lq[i]);
-          }
-        }
-        __threadfence();                        // statistics (and the tile) are visible device-wide before the arrival below
-        ptx::named_bar_sync(1, EPI_THREADS);
-        const int nrows_blk = 2 * ((g.M + 2 * BM - 1) / (2 * BM));  // counters per 128-row block, pair-padded (host: ln_scratch_layout)
-        if (ew == 0 && lane == 0) {
-          red_release_gpu_add(&g.ln_count[mb], 1);
-          uint32_t spins = 0;
-          while (ld_acquire_gpu(&g.ln_count[mb]) < LN_NB) {
-            __nanosleep(64);
-            if (++spins > (1u << 24)) __trap();  // a missing neighbour fails the launch instead of hanging the GPU
-          }
-        }
-        ptx::named_bar_sync(1, EPI_THREADS);
-        const int t = ew * 32 + lane;
-        if (t < BM) {
-          float sum = 0.f, sq = 0.f;
-          if (m0 + t < g.M) {
-            const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + (size_t)(m0 + t) * (2 * LN_NB));
-#pragma unroll
-            for (int i = 0; i < LN_NB; ++i) {
-              const float4 p = __ldcg(sp + i);  // two (sum, sq) pairs; written by other SMs: read at L2
-              sum += p.x + p.z;
-              sq += p.y + p.w;
-            }
-          }
-          const float mean = sum * (1.0f / LN_C);
-          const float var = fmaxf(sq * (1.0f / LN_C) - mean * mean, 0.f);
-          rowstat[t] = make_float2(mean, rsqrtf(var + g.ln_eps));
-        }
-        ptx::named_bar_sync(1, EPI_THREADS);
-        if (ew == 0 && lane == 0) {
-          // the last of the LN_NB CTAs to get here re-arms the counters for the next launch
-          if (atomicAdd(&g.ln_count[nrows_blk + mb], 1) == LN_NB - 1) {
-            g.ln_count[mb] = 0;
-            g.ln_count[nrows_blk + mb] = 0;
-          }
-        }
-        // normalise this CTA's 128 x 256 tile: a warp per row, 64 float4 per row = 2 per lane, R rows in flight
-        const int colq = nb * (BN / 4);  // first float4 column of the tile in a row of LN_C / 4
-        float4 ga[2], be[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          ga[i] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + colq + lane + 32 * i);
-          be[i] = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + colq + lane + 32 * i);
-        }
-        constexpr int R = 4;
-        const float4* tile4 = reinterpret_cast<const float4*>(ln_tile);
-#pragma unroll 1
-        for (int rp = 0; rp < BM / EPI_WARPS; rp += R) {
-          float4 v[R][2];
-#pragma unroll
-          for (int j = 0; j < R; ++j) {
-            const int r = ew + EPI_WARPS * (rp + j);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) v[j][i] = ptx::ld_global_hint(tile4 + r * (BN / 4) + lane + 32 * i, keep);
-          }
-#pragma unroll
-          for (int j = 0; j < R; ++j) {
-            const int r = ew + EPI_WARPS * (rp + j);
-            const float2 st = rowstat[r];
-            if (m0 + r < g.M) {
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                float4 y;
-                y.x = fmaf((v[j][i].x - st.x) * st.y, ga[i].x, be[i].x); y.y = fmaf((v[j][i].y - st.x) * st.y, ga[i].y, be[i].y);
-                y.z = fmaf((v[j][i].z - st.x) * st.y, ga[i].z, be[i].z); y.w = fmaf((v[j][i].w - st.x) * st.y, ga[i].w, be[i].w);
-                const size_t o = (size_t)(m0 + r) * (LN_C / 4) + colq + lane + 32 * i;
-                if (g.ln_out_f32) __stcs(reinterpret_cast<float4*>(g.ln_out_f32) + o, y);
-                if (g.ln_out_bf16) __stcs(reinterpret_cast<uint2*>(g.ln_out_bf16) + o, make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w)));
-              }
-            }
-          }
-        }
-        ptx::named_bar_sync(1, EPI_THREADS);  // tile scratch and rowstat may be overwritten by the next tile
       }
     }
+    if (ln && LN_DEFER && it_last >= 0) ln_finish(mu_p, nb_p, it_last & 1);
   }
 
   ptx::tc_fence_before();
@@ -576,7 +606,7 @@ LnScratch ln_scratch_layout(int M) {
   const size_t ctas = blocks * LN_NB < (size_t)num_sms() ? blocks * LN_NB + 1 : (size_t)num_sms();  // +1: pair grids are even
   LnScratch L;
   L.tiles = 0;
-  L.stats = ctas * BM * BN * sizeof(float);
+  L.stats = ctas * 2 * BM * BN * sizeof(float);
   L.count = L.stats + blocks * BM * 2 * LN_NB * sizeof(float2);
   L.total = L.count + ((2 * blocks * sizeof(int) + 255) & ~size_t(255));
   return L;

@@ -226,7 +226,8 @@ int avexk_conv1x1_bf16(const void* A, const void* W, int M, int N, int K, const 
 /* Depthwise k x k convolution (k = 3 | 5, stride 1 | 2, padding (k-1)/2) + folded BatchNorm + SiLU.
  * in [B,H,W,C] bf16, w_ckk [C,1,k,k] fp32 (torch layout), out [B,Ho,Wo,C] bf16, Ho = (H + 2p - k) / stride + 1.
  * se_sum [B,C] fp32 (may be NULL) receives sum over output pixels of the activated output (squeeze-excitation).
- * workspace >= C*k*k floats (repacked weights). */
+ * The sums are accumulated in 40.24 fixed point, so they are bit-reproducible from run to run.
+ * workspace >= 8*B*C + 4*C*k*k bytes (fixed-point accumulators, repacked weights). */
 int avexk_dwconv_nhwc(const void* in_bf16, int B, int H, int W, int C, int k, int stride, const float* w_ckk,
                       const float* scale, const float* shift, void* out_bf16, float* se_sum, void* workspace, void* stream);
 

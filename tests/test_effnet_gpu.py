@@ -106,7 +106,7 @@ def test_dwconv(lib, B, H, W, C, k, stride):
     Ho, Wo = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
     out = torch.empty(B, Ho, Wo, C, device="cuda", dtype=torch.bfloat16)
     se = torch.empty(B, C, device="cuda")
-    ws = torch.empty(C * k * k, device="cuda")
+    ws = torch.empty(2 * B * C + C * k * k, device="cuda")
     _check(lib.avexk_dwconv_nhwc(x.data_ptr(), B, H, W, C, k, stride, w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                  out.data_ptr(), se.data_ptr(), ws.data_ptr(), _stream()), lib)  # fmt: skip
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w, stride=stride, padding=p, groups=C)
