@@ -33,21 +33,26 @@ namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int CTRL_WARPS = 4;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle (register donors: setmaxnreg works per warpgroup)
-constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
 constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;  // 32 rows x 32 fp32, XOR-swizzled (no padding)
-constexpr int NTHREADS = 32 * (CTRL_WARPS + EPI_WARPS);
-constexpr int CTRL_REGS = 64, EPI_REGS = 216;  // 128 * 64 + 256 * 216 = 63488 <= 65536
 constexpr bool LN_DEFER = false;  // normalise tile i after tile i+1 has been drained (measured slower: 0.44 vs 0.39 ms on out_proj)
 constexpr int LN_C = 768, LN_NB = LN_C / BN;   // the fused LayerNorm epilogue is built for rows of 3 tiles
 
-template <bool PAIR>
+// EW epilogue warps: 8 for the residual / LayerNorm epilogue (216 registers each: two TMEM chunks and two residual chunks
+// in flight), 16 for the others (112 registers; twice the loads, stores and MUFU chains in flight per SM).
+template <bool PAIR, int EW>
 struct Cfg {
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int EPI_WARPS = EW, EPI_THREADS = EW * 32, NTHREADS = 32 * (CTRL_WARPS + EW);
+  static constexpr int CHUNKS = 32 / EW;  // 32-column chunks of the 256-column tile per epilogue warp
+  // setmaxnreg moves registers inside the CTA's launch allocation (threads x compiled count), it cannot grow it:
+  // EW = 8: 384 x 168 = 64512 >= 128*64 + 256*216 = 63488;  EW = 16: 640 x 96 = 61440 >= 128*56 + 512*104 = 60416
+  static constexpr int CTRL_REGS = EW == 8 ? 64 : 56, EPI_REGS = EW == 8 ? 216 : 104;
+  static constexpr int STAGES = PAIR ? (EW == 8 ? 6 : 5) : (EW == 8 ? 4 : 3);
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of W each CTA stages per k-block
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TX_BYTES = STAGE_BYTES * (PAIR ? 2 : 1);  // bytes landing on the (leader's) full barrier
   static constexpr int UM = PAIR ? 2 * BM : BM;                  // output rows per scheduling unit
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 256 + BM * 8;
+  static_assert(SMEM_BYTES <= 232448, "gemm: shared memory budget");
 };
 
 enum { MODE_PLAIN = 0, MODE_GELU = 1, MODE_RES = 2, MODE_CONV = 3 };
@@ -113,11 +118,12 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int MODE, bool PAIR>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int MODE, bool PAIR, int EW>
+__global__ void __launch_bounds__(32 * (CTRL_WARPS + EW), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
-  using C = Cfg<PAIR>;
-  constexpr int STAGES = C::STAGES;
+  using C = Cfg<PAIR, EW>;
+  constexpr int STAGES = C::STAGES, EPI_WARPS = C::EPI_WARPS, EPI_THREADS = C::EPI_THREADS, CHUNKS = C::CHUNKS;
+  static_assert(MODE != MODE_RES || EW == 8, "the residual / LayerNorm epilogue is written for 8 warps");
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment: required by the 128B swizzle pattern shared by TMA and the UMMA descriptors.  The offset is the
   // same in both CTAs of a pair (same kernel, same dynamic-smem base), which the pair MMA and multicast commits rely on.
@@ -177,7 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < CTRL_WARPS) {
-    ptx::setmaxnreg_dec<CTRL_REGS>();
+    ptx::setmaxnreg_dec<C::CTRL_REGS>();
     if (warp == 0) {
       // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
       if (lane == 0) {
@@ -252,8 +258,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================== epilogue (warps 4..11) =====================
     // Two warps per TMEM lane quarter; each owns four of the tile's eight 32-column chunks.  The TMEM load and the fp32
     // residual of the NEXT chunk are in flight while the current chunk is processed.
-    ptx::setmaxnreg_inc<EPI_REGS>();
-    const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;
+    ptx::setmaxnreg_inc<C::EPI_REGS>();
+    const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;  // half: which group of CHUNKS chunks
     float* stg = stg_base + ew * (32 * 32);
     const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
     const bool has_res = MODE == MODE_RES && g.residual != nullptr;
@@ -279,7 +285,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     };
 
-    float4 bias_t[4], scale_t[4];  // this lane's bias (and BN scale) columns of the tile's four chunks, loaded ahead of the accumulator
+    float4 bias_t[CHUNKS], scale_t[CHUNKS];  // this lane's bias (and BN scale) columns of the tile's four chunks, loaded ahead of the accumulator
     auto process = [&](const uint32_t (&r)[32], const float4 (&res)[8], int mu, int nb, int c, const float4 bias4, const float4 scale4) {
       const int col0 = nb * BN + c * 32;
       if (col0 >= g.N) return;  // warp-uniform
@@ -446,7 +452,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     {
       int mu, nb;
       const bool v0 = tile_of(0, mu, nb);
-      load_res(v0, mu, nb, half * 4, res_a);
+      load_res(v0, mu, nb, half * CHUNKS, res_a);
     }
     for (int it = 0;; ++it) {
       int mu, nb;
@@ -457,8 +463,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
       if (ln) ln_cur = ln_tile + (size_t)(it & 1) * BM * BN;
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) {
-        const int cc = nb * BN + (half * 4 + ci) * 32 + csub * 4;
+      for (int ci = 0; ci < CHUNKS; ++ci) {
+        const int cc = nb * BN + (half * CHUNKS + ci) * 32 + csub * 4;
         bias_t[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
         scale_t[ci] = make_float4(1.f, 1.f, 1.f, 1.f);
         if (g.bias != nullptr && cc < g.N) bias_t[ci] = __ldg(reinterpret_cast<const float4*>(g.bias + cc));
@@ -466,25 +472,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 128;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (CHUNKS * 32);
+      const int c0 = half * CHUNKS;
       uint32_t ra[32], rb[32];
       ptx::tmem_ld_32x32(t_addr, ra);
-      // chunk 0
-      ptx::tmem_ld_wait();
-      ptx::tmem_ld_32x32(t_addr + 32, rb);
-      load_res(true, mu, nb, half * 4 + 1, res_b);
-      process(ra, res_a, mu, nb, half * 4, bias_t[0], scale_t[0]);
-      // chunk 1
-      ptx::tmem_ld_wait();
-      ptx::tmem_ld_32x32(t_addr + 64, ra);
-      load_res(true, mu, nb, half * 4 + 2, res_a);
-      process(rb, res_b, mu, nb, half * 4 + 1, bias_t[1], scale_t[1]);
-      // chunk 2
-      ptx::tmem_ld_wait();
-      ptx::tmem_ld_32x32(t_addr + 96, rb);
-      load_res(true, mu, nb, half * 4 + 3, res_b);
-      process(ra, res_a, mu, nb, half * 4 + 2, bias_t[2], scale_t[2]);
-      // chunk 3: every TMEM read of this accumulator has completed -> hand it back to the MMA warp before the last chunk
+      if (CHUNKS == 4) {
+        // chunk 0
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(t_addr + 32, rb);
+        load_res(true, mu, nb, c0 + 1, res_b);
+        process(ra, res_a, mu, nb, c0, bias_t[0], scale_t[0]);
+        // chunk 1
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(t_addr + 64, ra);
+        load_res(true, mu, nb, c0 + 2, res_a);
+        process(rb, res_b, mu, nb, c0 + 1, bias_t[1], scale_t[1]);
+        // chunk 2
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(t_addr + 96, rb);
+        load_res(true, mu, nb, c0 + 3, res_b);
+        process(ra, res_a, mu, nb, c0 + 2, bias_t[CHUNKS - 2], scale_t[CHUNKS - 2]);
+      } else {
+        // chunk 0 of 2
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(t_addr + 32, rb);
+        process(ra, res_a, mu, nb, c0, bias_t[0], scale_t[0]);
+      }
+      // last chunk: every TMEM read of this accumulator has completed -> hand it back to the MMA warp first
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
@@ -492,8 +506,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (PAIR) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
         else ptx::mbar_arrive(&tempty_bar[acc]);
       }
-      load_res(valid_n, mu_n, nb_n, half * 4, res_a);
-      process(rb, res_b, mu, nb, half * 4 + 3, bias_t[3], scale_t[3]);
+      load_res(valid_n, mu_n, nb_n, c0, res_a);
+      process(rb, res_b, mu, nb, c0 + CHUNKS - 1, bias_t[CHUNKS - 1], scale_t[CHUNKS - 1]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 
       if (ln) {
@@ -537,10 +551,12 @@ bool use_pair() {
 
 template <int MODE, bool PAIR>
 int launch_mode(const void* A, long long lda, const void* W, long long ldw, const GemmArgs& g, cudaStream_t st) {
-  using C = Cfg<PAIR>;
+  constexpr int EW = MODE == MODE_RES ? 8 : 16;
+  using C = Cfg<PAIR, EW>;
+  constexpr int NTHREADS = C::NTHREADS;
   static bool attr_set = false;
   if (!attr_set) {
-    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<MODE, PAIR, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ma, mb;
@@ -566,9 +582,9 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR>, ma, mb, g));
+    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW>, ma, mb, g));
   } else {
-    gemm_bf16_kernel<MODE, PAIR><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, g);
+    gemm_bf16_kernel<MODE, PAIR, EW><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, g);
   }
   prof_end(st);
   AVEXK_LAUNCH_CHECK();
