@@ -231,9 +231,9 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
     return gemm_bf16_launch(A, K, W, K, (int)M, Nn, K, bias, gelu, raw, res, rs, o, Nn, obf, st);
   };
   // GEMM + DeepNorm residual + LayerNorm in one launch when the width matches the fused epilogue (BEATs-base: 768)
-  // AVEXK_FUSE_LN: 0 = separate LayerNorm launches, 1 (default) = fc2 only, 2 = out_proj and fc2.  Measured at config #2:
-  // 35.9 / 35.2 / 35.4 ms per step: the K=768 out_proj tile is too short to hide the statistics exchange.
-  static const int fuse_level = [] { const char* e = getenv("AVEXK_FUSE_LN"); return e ? atoi(e) : 1; }();
+  // AVEXK_FUSE_LN: 0 = separate LayerNorm launches, 1 = fc2 only, 2 (default) = out_proj and fc2.  Measured at config #2
+  // with the TMEM-resident LayerNorm epilogue: 33.1 ms (1) vs 32.8 ms (2) per step.
+  static const int fuse_level = [] { const char* e = getenv("AVEXK_FUSE_LN"); return e ? atoi(e) : 2; }();
   const bool fuse_ln = C == 768 && fuse_level > 0;
   int ln_first = 1;  // the scratch counters are zeroed once per forward; every launch leaves them zero
   auto gemm_ln = [&](const void* A, int K, const __nv_bfloat16* W, const float* bias, float* raw, const float* gamma, const float* beta,

@@ -7,20 +7,24 @@
 // (bias, exact GELU, DeepNorm residual `residual * alpha + x`, backbone.py:360,:372, and the post-LN LayerNorm of
 // backbone.py:362,:373), fused in the epilogue.  Also the 1x1 convolutions of EfficientNet (MODE_CONV).
 //
-// Structure (one CTA per SM, 320 threads; PAIR = two CTAs of a cluster drive one 256x256 tile with cta_group::2):
+// Structure (one CTA per SM; PAIR = two CTAs of a cluster drive one 256x256 tile with cta_group::2):
 //   warp 0      TMA producer : cp.async.bulk.tensor 128x64 (A) + 256x64 (W; 128x64 per CTA of a pair) bf16 tiles,
-//                              128B swizzle, 4-stage (6-stage for a pair) mbarrier ring
+//                              128B swizzle, mbarrier ring
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma 128x256x16 (cta_group::1) or 256x256x16
 //                              (cta_group::2, leader CTA only; each CTA holds half of W's rows, so the shared-memory
 //                              operand traffic per SM drops from 96 to 64 bytes/clk), commits to mbarriers
-//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 from TMEM (next chunk in flight while this one is processed) ->
-//                              per-warp smem transposition -> coalesced 16-byte global stores; the fp32 residual is
-//                              register-prefetched one chunk ahead
+//   warps 2-3   idle register donors (setmaxnreg works per warpgroup)
+//   warps 4..   epilogue, two flavours:
+//     bias / GELU / conv (16 warps): tcgen05.ld 32x32b.x32 (next chunk in flight) -> per-warp smem transposition ->
+//                              coalesced 16-byte global stores
+//     residual / LayerNorm (8 warps, MODE_RES): everything stays in the TMEM layout (lane = output row).  Each warp
+//                              streams its 32x32 fp32 residual boxes in by TMA (3 deep), adds bias + alpha * residual, and
+//                              either TMA-stores the result, or -- fused LayerNorm -- accumulates the row's (sum, sum of
+//                              squares) in registers, parks the pre-LN values back in TMEM (tcgen05.st), swaps the row
+//                              statistics with the two CTAs holding the other column tiles of the same rows through L2,
+//                              re-reads TMEM, normalises and writes fp32 (TMA store) + bf16: the pre-LN [M,768] tensor
+//                              never exists in memory and the separate LayerNorm launch disappears.
 //   TMEM: 512 columns = two 128x256 fp32 accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Fused LayerNorm (MODE_RES, N == 768): a CTA walks the three 256-column tiles of a 128-row block back to back, parks
-// the pre-LN sums in a per-CTA scratch that stays L2-resident (148 x 393 KB), and its epilogue warps normalise the
-// rows from L2 while the tensor core is already on the next row block: the [M,768] fp32 pre-LN tensor never makes the
-// round trip through HBM and the separate LayerNorm launch disappears.
 // Roofline: dense bf16 tensor pipe; algorithmic FLOPs = 2*M*N*K.
 #include <stdlib.h>
 
@@ -32,30 +36,33 @@ namespace avexk {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int CTRL_WARPS = 4;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle (register donors: setmaxnreg works per warpgroup)
-constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;  // 32 rows x 32 fp32, XOR-swizzled (no padding)
-constexpr bool LN_DEFER = false;  // normalise tile i after tile i+1 has been drained (measured slower: 0.44 vs 0.39 ms on out_proj)
-constexpr int LN_C = 768, LN_NB = LN_C / BN;   // the fused LayerNorm epilogue is built for rows of 3 tiles
+constexpr int CTRL_WARPS = 4;
+constexpr int STG_BYTES_PER_WARP = 32 * 32 * 4;  // 32 rows x 32 fp32 (128-byte rows), XOR-swizzled
+constexpr int LN_C = 768, LN_NB = LN_C / BN;     // the fused LayerNorm epilogue is built for rows of 3 tiles
 
-// EW epilogue warps: 8 for the residual / LayerNorm epilogue (216 registers each: two TMEM chunks and two residual chunks
-// in flight), 16 for the others (112 registers; twice the loads, stores and MUFU chains in flight per SM).
-template <bool PAIR, int EW>
+enum { MODE_PLAIN = 0, MODE_GELU = 1, MODE_RES = 2, MODE_CONV = 3 };
+
+// DEEPK (MODE_RES with a long K loop, fc2): the tile's MMA time hides the epilogue, so shared memory goes to a fourth
+// operand stage instead of a third residual box per warp.
+template <bool PAIR, int EW, int MODE, bool DEEPK>
 struct Cfg {
   static constexpr int EPI_WARPS = EW, EPI_THREADS = EW * 32, NTHREADS = 32 * (CTRL_WARPS + EW);
   static constexpr int CHUNKS = 32 / EW;  // 32-column chunks of the 256-column tile per epilogue warp
   // setmaxnreg moves registers inside the CTA's launch allocation (threads x compiled count), it cannot grow it:
   // EW = 8: 384 x 168 = 64512 >= 128*64 + 256*216 = 63488;  EW = 16: 640 x 96 = 61440 >= 128*56 + 512*104 = 60416
   static constexpr int CTRL_REGS = EW == 8 ? 64 : 56, EPI_REGS = EW == 8 ? 216 : 104;
-  static constexpr int STAGES = PAIR ? (EW == 8 ? 6 : 5) : (EW == 8 ? 4 : 3);
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of W each CTA stages per k-block
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  // MODE_RES spends 96 KB of shared memory on the residual ring, so it keeps fewer operand stages
+  static constexpr int RES_DEPTH = (PAIR && DEEPK) ? 2 : 3;  // residual boxes in flight per epilogue warp (MODE_RES)
+  static constexpr int STAGES = MODE == MODE_RES ? (PAIR ? (DEEPK ? 4 : 3) : 2) : (PAIR ? (EW == 8 ? 6 : 5) : (EW == 8 ? 4 : 3));
   static constexpr int TX_BYTES = STAGE_BYTES * (PAIR ? 2 : 1);  // bytes landing on the (leader's) full barrier
   static constexpr int UM = PAIR ? 2 * BM : BM;                  // output rows per scheduling unit
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP + 256 + BM * 8;
+  static constexpr int RES_BYTES = MODE == MODE_RES ? EW * RES_DEPTH * STG_BYTES_PER_WARP : 0;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_RES = OFF_STG + EW * STG_BYTES_PER_WARP, OFF_BAR = OFF_RES + RES_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
   static_assert(SMEM_BYTES <= 232448, "gemm: shared memory budget");
 };
-
-enum { MODE_PLAIN = 0, MODE_GELU = 1, MODE_RES = 2, MODE_CONV = 3 };
 
 struct GemmArgs {
   int M, N, K;
@@ -74,11 +81,10 @@ struct GemmArgs {
   const float* ln_gamma;
   const float* ln_beta;
   float ln_eps;
-  float* ln_out_f32;
+  float* ln_out_f32;  // written through map_y
   __nv_bfloat16* ln_out_bf16;
-  float* ln_tiles;   // [gridDim.x][2][128][256] fp32: this CTA's last two pre-LN tiles, re-read from L2 microseconds later
-  float2* ln_stats;  // [ceil(M/128)*128][2*LN_NB] (sum, sum of squares) over 128 columns of a row
-  int* ln_count;     // [2][ceil(M/128)]: arrivals / departures per 128-row block; zero before and after every launch
+  float2* ln_stats;  // [ceil(M/256)*256][2*LN_NB] (sum, sum of squares) over 128 columns of a row
+  int* ln_count;     // [2][2*ceil(M/256)]: arrivals / departures per 128-row block; zero before and after every launch
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -117,11 +123,21 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
-template <int MODE, bool PAIR, int EW>
+template <int MODE, bool PAIR, int EW, bool DEEPK>
 __global__ void __launch_bounds__(32 * (CTRL_WARPS + EW), 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
-  using C = Cfg<PAIR, EW>;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_y, const GemmArgs g) {
+  using C = Cfg<PAIR, EW, MODE, DEEPK>;
+  constexpr int RES_DEPTH = C::RES_DEPTH;
   constexpr int STAGES = C::STAGES, EPI_WARPS = C::EPI_WARPS, EPI_THREADS = C::EPI_THREADS, CHUNKS = C::CHUNKS;
   static_assert(MODE != MODE_RES || EW == 8, "the residual / LayerNorm epilogue is written for 8 warps");
   extern __shared__ unsigned char smem_raw[];
@@ -129,14 +145,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // same in both CTAs of a pair (same kernel, same dynamic-smem base), which the pair MMA and multicast commits rely on.
   unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
-  float* stg_base = reinterpret_cast<float*>(smem + STAGES * C::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::STAGE_BYTES + EPI_WARPS * STG_BYTES_PER_WARP);
+  float* stg_base = reinterpret_cast<float*>(smem + C::OFF_STG);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* full_bar = bars;                      // [STAGES]  (pair: only the leader's are waited on)
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]       (pair: the leader's collect both CTAs' epilogue warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float2* rowstat = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [BM] (mean, rstd), fused LN
+  uint64_t* res_bar = bars + 32;                  // [EPI_WARPS][RES_DEPTH] residual boxes landed (MODE_RES)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
@@ -144,7 +160,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int num_units = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int m_units = (g.M + C::UM - 1) / C::UM, n_blocks = (g.N + BN - 1) / BN;
   const int num_tiles = m_units * n_blocks, num_kb = (g.K + BK - 1) / BK;
-  const bool ln = MODE == MODE_RES && g.ln_gamma != nullptr;
   // iteration -> tile of this scheduling unit: tiles round-robin over units, n fastest, so the units working on the n tiles
   // of one row block run side by side (they share the A rows in L2 and, with the fused LayerNorm, exchange row statistics)
   auto tile_of = [&](int it, int& mu, int& nb) -> bool {
@@ -157,6 +172,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
+    if (MODE == MODE_RES) {
+      ptx::prefetch_tensormap(&map_res);
+      ptx::prefetch_tensormap(&map_y);
+    }
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -165,6 +184,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], EPI_WARPS * (PAIR ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     }
+    if (MODE == MODE_RES)
+      for (int i = 0; i < EPI_WARPS * RES_DEPTH; ++i) ptx::mbar_init(&res_bar[i], 1);
     ptx::fence_barrier_init();
   }
   __syncwarp();
@@ -254,42 +275,211 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if constexpr (MODE == MODE_RES) {
+    // ===================== residual / LayerNorm epilogue (warps 4..11): lane = output row =====================
+    // Warp (quarter q, half h) owns rows 32q..32q+31 and the four 32-column chunks 4h..4h+3 of every tile.  Its work is a
+    // flat sequence of 32x32 fp32 boxes (4 per tile); the residuals of the next RES_DEPTH-1 boxes are in flight (TMA) while box n is processed.
+    ptx::setmaxnreg_inc<C::EPI_REGS>();
+    const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;
+    const bool ln = g.ln_gamma != nullptr;
+    const bool has_res = g.residual != nullptr;
+    const uint32_t ybuf = ptx::smem_u32(stg_base) + ew * STG_BYTES_PER_WARP;                       // staging of one output box
+    const uint32_t rbuf = ptx::smem_u32(smem + C::OFF_RES) + ew * (RES_DEPTH * STG_BYTES_PER_WARP);  // residual ring
+    uint64_t* rbar = res_bar + ew * RES_DEPTH;
+    const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    const uint32_t rowoff = lane * 128, sw = lane & 7;  // 128-byte rows; 16-byte chunk j of row r is stored at chunk j ^ (r & 7)
+    const int nrows_blk = 2 * ((g.M + 2 * BM - 1) / (2 * BM));  // counters per 128-row block, pair-padded (host: ln_scratch_layout)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    // residual box n of this warp (tile n / 4, chunk 4h + n % 4) -> ring slot n % RES_DEPTH.  The caller has made sure
+    // (__syncwarp) that every lane is done reading the slot being overwritten.
+    auto issue_res = [&](int n) {
+      int mu, nb;
+      if (!has_res || lane != 0 || !tile_of(n >> 2, mu, nb)) return;
+      const int s = n % RES_DEPTH;
+      ptx::fence_proxy_async();  // the generic-proxy reads of this slot are ordered before the async-proxy overwrite
+      ptx::mbar_arrive_expect_tx(&rbar[s], STG_BYTES_PER_WARP);
+      ptx::tma_load_2d_s(rbuf + s * STG_BYTES_PER_WARP, &map_res, &rbar[s], nb * BN + (half * 4 + (n & 3)) * 32,
+                         mu * C::UM + static_cast<int>(rank) * BM + quarter * 32);
+    };
+    // stage a finished 32x32 fp32 box (this lane's row in v) and hand it to the TMA engine
+    auto store_box = [&](const float (&v)[32], int col, int row) {
+      if (lane == 0) ptx::tma_store_wait_read();  // the previous box has left the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128f(ybuf + rowoff + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      ptx::fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d_s(&map_y, ybuf, col, row);  // rows >= M / columns >= N are clipped by the tensor map
+        ptx::tma_store_commit();
+      }
+    };
+
+#pragma unroll
+    for (int n = 0; n < RES_DEPTH - 1; ++n) issue_res(n);
+    for (int it = 0;; ++it) {
+      int mu, nb;
+      if (!tile_of(it, mu, nb)) break;
+      const int m0 = mu * C::UM + static_cast<int>(rank) * BM, row0 = m0 + quarter * 32, grow = row0 + lane;
+      const bool row_ok = grow < g.M;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 128;
+      float sum = 0.f, sq = 0.f;
+      // ---- pass 1: v = acc + bias + alpha * residual ------------------------------------------------------------
+#pragma unroll 1
+      for (int ci = 0; ci < 4; ++ci) {
+        const int n = it * 4 + ci, s = n % RES_DEPTH;
+        const int col0 = nb * BN + (half * 4 + ci) * 32;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + ci * 32, r);
+        issue_res(n + RES_DEPTH - 1);  // its slot held box n - 1, released by the __syncwarp that ended the previous iteration
+        if (has_res) ptx::mbar_wait(&rbar[s], (n / RES_DEPTH) & 1);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);  // warp-uniform address
+          v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+        }
+        if (g.raw_out != nullptr && row_ok) {  // hook on the Linear (fc2): rare, so plain per-row stores
+          float4* dst = reinterpret_cast<float4*>(g.raw_out + (size_t)grow * g.N + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q = lds128f(rbuf + s * STG_BYTES_PER_WARP + rowoff + ((j ^ sw) << 4));
+            v[4 * j] = fmaf(g.res_scale, q.x, v[4 * j]);
+            v[4 * j + 1] = fmaf(g.res_scale, q.y, v[4 * j + 1]);
+            v[4 * j + 2] = fmaf(g.res_scale, q.z, v[4 * j + 2]);
+            v[4 * j + 3] = fmaf(g.res_scale, q.w, v[4 * j + 3]);
+          }
+        }
+        if (ln) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sum += v[j];
+            sq = fmaf(v[j], v[j], sq);
+            r[j] = __float_as_uint(v[j]);
+          }
+          ptx::tmem_st_32x32(t_addr + ci * 32, r);  // park the pre-LN values where they came from
+        } else if (g.out != nullptr) {
+          store_box(v, col0, row0);
+        }
+        __syncwarp();  // every lane is done with residual slot s
+      }
+      if (!ln) {
+        // all TMEM reads of this accumulator have completed (wait::ld in the last iteration)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
+          else ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+      } else {
+        // ---- fused LayerNorm (backbone.py:362,:373): the LN_NB CTAs holding the column tiles of these 128 rows swap
+        // per-row (sum, sum of squares) through L2.  Requires all CTAs of the grid to be co-resident (grid <= #SMs, one
+        // CTA per SM): a CTA publishes its own statistics before it waits for its neighbours'.
+        const int mb = m0 / BM;
+        if (row_ok) g.ln_stats[(size_t)grow * (2 * LN_NB) + nb * 2 + half] = make_float2(sum, sq);
+        ptx::tmem_st_wait();
+        // CTA barrier + release at gpu scope by the announcing thread: the other warps' statistics are ordered before the
+        // arrival by cumulativity (no per-thread __threadfence())
+        ptx::named_bar_sync(1, EPI_THREADS);
+        if (ew == 0 && lane == 0) {
+          red_release_gpu_add(&g.ln_count[mb], 1);
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(&g.ln_count[mb]) < LN_NB) {
+            __nanosleep(32);
+            if (++spins > (1u << 24)) __trap();  // a missing neighbour fails the launch instead of hanging the GPU
+          }
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);
+        float mean = 0.f, rstd = 0.f;
+        {
+          float s1 = 0.f, s2 = 0.f;
+          if (row_ok) {
+            const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + (size_t)grow * (2 * LN_NB));
+#pragma unroll
+            for (int i = 0; i < LN_NB; ++i) {
+              const float4 p = __ldcg(sp + i);  // two (sum, sq) pairs; written by other SMs: read at L2
+              s1 += p.x + p.z;
+              s2 += p.y + p.w;
+            }
+          }
+          mean = s1 * (1.0f / LN_C);
+          rstd = rsqrtf(fmaxf(s2 * (1.0f / LN_C) - mean * mean, 0.f) + g.ln_eps);
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);  // every statistic of this row block has been read
+        if (ew == 0 && lane == 0) {
+          // the last of the LN_NB CTAs to get here re-arms the counters for the next launch
+          if (atomicAdd(&g.ln_count[nrows_blk + mb], 1) == LN_NB - 1) {
+            g.ln_count[mb] = 0;
+            g.ln_count[nrows_blk + mb] = 0;
+          }
+        }
+        // ---- pass 2: y = (v - mean) * rstd * gamma + beta ----------------------------------------------------
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col0 = nb * BN + (half * 4 + ci) * 32;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_addr + ci * 32, r);
+          ptx::tmem_ld_wait();
+          if (ci == 3) {  // the accumulator is drained: hand it back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
+              else ptx::mbar_arrive(&tempty_bar[acc]);
+            }
+          }
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(g.ln_gamma + col0) + j);  // warp-uniform addresses
+            const float4 be = __ldg(reinterpret_cast<const float4*>(g.ln_beta + col0) + j);
+            y[4 * j] = fmaf((__uint_as_float(r[4 * j]) - mean) * rstd, ga.x, be.x);
+            y[4 * j + 1] = fmaf((__uint_as_float(r[4 * j + 1]) - mean) * rstd, ga.y, be.y);
+            y[4 * j + 2] = fmaf((__uint_as_float(r[4 * j + 2]) - mean) * rstd, ga.z, be.z);
+            y[4 * j + 3] = fmaf((__uint_as_float(r[4 * j + 3]) - mean) * rstd, ga.w, be.w);
+          }
+          if (g.ln_out_bf16 != nullptr && row_ok) {  // 64 contiguous bytes per row: two full sectors
+            uint4* dst = reinterpret_cast<uint4*>(g.ln_out_bf16 + (size_t)grow * LN_C + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              __stcs(dst + j, make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
+                                         pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7])));
+          }
+          if (g.ln_out_f32 != nullptr) store_box(y, col0, row0);
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) ptx::tma_store_wait_all();  // the bulk stores must have been performed before the CTA exits
   } else {
-    // ===================== epilogue (warps 4..11) =====================
-    // Two warps per TMEM lane quarter; each owns four of the tile's eight 32-column chunks.  The TMEM load and the fp32
-    // residual of the NEXT chunk are in flight while the current chunk is processed.
+    // ===================== bias / GELU / conv epilogue (warps 4..19) =====================
+    // Four warps per TMEM lane quarter; each owns CHUNKS of the tile's eight 32-column chunks.  The TMEM load of the next
+    // chunk is in flight while the current one is transposed through shared memory and stored with 16-byte coalesced writes.
     ptx::setmaxnreg_inc<C::EPI_REGS>();
     const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;  // half: which group of CHUNKS chunks
     float* stg = stg_base + ew * (32 * 32);
     const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
-    const bool has_res = MODE == MODE_RES && g.residual != nullptr;
-    float* ln_tile = ln ? g.ln_tiles + static_cast<size_t>(blockIdx.x) * 2 * BM * BN : nullptr;  // two tiles: i is normalised after i+1 is drained
-    float* ln_cur = ln_tile;
     const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
-    // the pre-LN tile is written, exchanged on and re-read within microseconds: keep it in L2 while the operands stream by
-    const uint64_t keep = ln ? ptx::policy_evict_last() : 0ull;
-    float ls[8], lq[8];  // fused LN: this lane's partial (sum, sum of squares) of rows i*4+rsub over the warp's 128 columns
     int acc = 0;
     uint32_t acc_phase = 0;
 
-    auto load_res = [&](bool valid, int mu, int nb, int c, float4 (&dst)[8]) {
-      if (MODE != MODE_RES) return;
-      const int cc = nb * BN + c * 32 + csub * 4;
-      const int row0 = mu * C::UM + static_cast<int>(rank) * BM + quarter * 32;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int grow = row0 + i * 4 + rsub;
-        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_res && valid && grow < g.M && cc < g.N)
-          dst[i] = __ldcs(reinterpret_cast<const float4*>(g.residual + (size_t)grow * g.N + cc));  // read once; may be rewritten by this CTA's LayerNorm
-      }
-    };
-
-    float4 bias_t[CHUNKS], scale_t[CHUNKS];  // this lane's bias (and BN scale) columns of the tile's four chunks, loaded ahead of the accumulator
-    auto process = [&](const uint32_t (&r)[32], const float4 (&res)[8], int mu, int nb, int c, const float4 bias4, const float4 scale4) {
+    auto process = [&](const uint32_t (&r)[32], int mu, int nb, int c, const float4 bias4, const float4 scale4) {
       const int col0 = nb * BN + c * 32;
       if (col0 >= g.N) return;  // warp-uniform
-      const int lrow0 = quarter * 32, row0 = mu * C::UM + static_cast<int>(rank) * BM + lrow0;
+      const int row0 = mu * C::UM + static_cast<int>(rank) * BM + quarter * 32;
       // lane owns one row: park its 32 columns (XOR-swizzled 16-byte slots), re-read so 8 lanes cover a 128 B row segment
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -326,16 +516,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               v = make_float4(g0.x, g0.y, g1.x, g1.y);
             }
             if (g.raw_out != nullptr) *reinterpret_cast<float4*>(g.raw_out + off) = v;
-            if (MODE == MODE_RES) {
-              v.x = fmaf(g.res_scale, res[i].x, v.x); v.y = fmaf(g.res_scale, res[i].y, v.y);
-              v.z = fmaf(g.res_scale, res[i].z, v.z); v.w = fmaf(g.res_scale, res[i].w, v.w);
-            }
           }
-          if (ln) {
-            ptx::st_global_hint(ln_cur + (lrow0 + rr) * BN + (c * 32 + csub * 4), v, keep);
-            ls[i] += (v.x + v.y) + (v.z + v.w);
-            lq[i] = fmaf(v.x, v.x, lq[i]); lq[i] = fmaf(v.y, v.y, lq[i]); lq[i] = fmaf(v.z, v.z, lq[i]); lq[i] = fmaf(v.w, v.w, lq[i]);
-          } else if (g.out != nullptr) {
+          if (g.out != nullptr) {
             const size_t oo = (size_t)grow * g.ldo + cc;
             if (g.out_bf16) {
               uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -349,119 +531,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
     };
 
-    // publish this warp's partial row statistics of the tile just drained and announce the tile (fused LN, pass 1 tail)
-    auto ln_publish = [&](int mu, int nb) {
-      const int m0 = mu * C::UM + static_cast<int>(rank) * BM, mb = m0 / BM;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          ls[i] += __shfl_xor_sync(0xffffffffu, ls[i], o);
-          lq[i] += __shfl_xor_sync(0xffffffffu, lq[i], o);
-        }
-      }
-      if (csub == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int grow = m0 + quarter * 32 + i * 4 + rsub;
-          if (grow < g.M) g.ln_stats[(size_t)grow * (2 * LN_NB) + nb * 2 + half] = make_float2(ls[i], lq[i]);
-        }
-      }
-      // CTA barrier + release at gpu scope by the announcing thread: the statistics written by the other warps are ordered
-      // before the arrival by cumulativity, so no per-thread __threadfence() (a full memory barrier per warp) is needed
-      ptx::named_bar_sync(1, EPI_THREADS);
-      if (ew == 0 && lane == 0) red_release_gpu_add(&g.ln_count[mb], 1);
-    };
-    // wait for the neighbours' statistics of tile (mu, nb), then normalise this CTA's copy of it (fused LN, pass 2)
-    auto ln_finish = [&](int mu, int nb, int buf) {
-      const int m0 = mu * C::UM + static_cast<int>(rank) * BM, mb = m0 / BM;
-      const int nrows_blk = 2 * ((g.M + 2 * BM - 1) / (2 * BM));  // counters per 128-row block, pair-padded (host: ln_scratch_layout)
-      if (ew == 0 && lane == 0) {
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(&g.ln_count[mb]) < LN_NB) {
-          __nanosleep(32);
-          if (++spins > (1u << 24)) __trap();  // a missing neighbour fails the launch instead of hanging the GPU
-        }
-      }
-      ptx::named_bar_sync(1, EPI_THREADS);
-      const int t = ew * 32 + lane;
-      if (t < BM) {
-        float sum = 0.f, sq = 0.f;
-        if (m0 + t < g.M) {
-          const float4* sp = reinterpret_cast<const float4*>(g.ln_stats + (size_t)(m0 + t) * (2 * LN_NB));
-#pragma unroll
-          for (int i = 0; i < LN_NB; ++i) {
-            const float4 p = __ldcg(sp + i);  // two (sum, sq) pairs; written by other SMs: read at L2
-            sum += p.x + p.z;
-            sq += p.y + p.w;
-          }
-        }
-        const float mean = sum * (1.0f / LN_C);
-        const float var = fmaxf(sq * (1.0f / LN_C) - mean * mean, 0.f);
-        rowstat[t] = make_float2(mean, rsqrtf(var + g.ln_eps));
-      }
-      ptx::named_bar_sync(1, EPI_THREADS);
-      if (ew == 0 && lane == 0) {
-        // the last of the LN_NB CTAs to get here re-arms the counters for the next launch
-        if (atomicAdd(&g.ln_count[nrows_blk + mb], 1) == LN_NB - 1) {
-          g.ln_count[mb] = 0;
-          g.ln_count[nrows_blk + mb] = 0;
-        }
-      }
-      // normalise the 128 x 256 tile: a warp per row, 64 float4 per row = 2 per lane, R rows in flight
-      const int colq = nb * (BN / 4);  // first float4 column of the tile in a row of LN_C / 4
-      float4 ga[2], be[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        ga[i] = __ldg(reinterpret_cast<const float4*>(g.ln_gamma) + colq + lane + 32 * i);
-        be[i] = __ldg(reinterpret_cast<const float4*>(g.ln_beta) + colq + lane + 32 * i);
-      }
-      constexpr int R = 4;
-      const float4* tile4 = reinterpret_cast<const float4*>(ln_tile + (size_t)buf * BM * BN);
-#pragma unroll 1
-      for (int rp = 0; rp < BM / EPI_WARPS; rp += R) {
-        float4 v[R][2];
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int r = ew + EPI_WARPS * (rp + j);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) v[j][i] = ptx::ld_global_hint(tile4 + r * (BN / 4) + lane + 32 * i, keep);
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int r = ew + EPI_WARPS * (rp + j);
-          const float2 st = rowstat[r];
-          if (m0 + r < g.M) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              float4 y;
-              y.x = fmaf((v[j][i].x - st.x) * st.y, ga[i].x, be[i].x); y.y = fmaf((v[j][i].y - st.x) * st.y, ga[i].y, be[i].y);
-              y.z = fmaf((v[j][i].z - st.x) * st.y, ga[i].z, be[i].z); y.w = fmaf((v[j][i].w - st.x) * st.y, ga[i].w, be[i].w);
-              const size_t o = (size_t)(m0 + r) * (LN_C / 4) + colq + lane + 32 * i;
-              if (g.ln_out_f32) __stcs(reinterpret_cast<float4*>(g.ln_out_f32) + o, y);
-              if (g.ln_out_bf16) __stcs(reinterpret_cast<uint2*>(g.ln_out_bf16) + o, make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w)));
-            }
-          }
-        }
-      }
-      ptx::named_bar_sync(1, EPI_THREADS);  // rowstat and (two tiles on) this scratch buffer may be overwritten
-    };
-
-    float4 res_a[8], res_b[8];
-    int mu_p = 0, nb_p = 0, it_last = -1;
-    {
-      int mu, nb;
-      const bool v0 = tile_of(0, mu, nb);
-      load_res(v0, mu, nb, half * CHUNKS, res_a);
-    }
+    float4 bias_t[CHUNKS], scale_t[CHUNKS];  // this lane's bias (and BN scale) columns, loaded ahead of the accumulator
     for (int it = 0;; ++it) {
       int mu, nb;
       if (!tile_of(it, mu, nb)) break;
-      int mu_n, nb_n;
-      const bool valid_n = tile_of(it + 1, mu_n, nb_n);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ls[i] = lq[i] = 0.f;
-      if (ln) ln_cur = ln_tile + (size_t)(it & 1) * BM * BN;
 #pragma unroll
       for (int ci = 0; ci < CHUNKS; ++ci) {
         const int cc = nb * BN + (half * CHUNKS + ci) * 32 + csub * 4;
@@ -477,26 +550,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t ra[32], rb[32];
       ptx::tmem_ld_32x32(t_addr, ra);
       if (CHUNKS == 4) {
-        // chunk 0
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x32(t_addr + 32, rb);
-        load_res(true, mu, nb, c0 + 1, res_b);
-        process(ra, res_a, mu, nb, c0, bias_t[0], scale_t[0]);
-        // chunk 1
+        process(ra, mu, nb, c0, bias_t[0], scale_t[0]);
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x32(t_addr + 64, ra);
-        load_res(true, mu, nb, c0 + 2, res_a);
-        process(rb, res_b, mu, nb, c0 + 1, bias_t[1], scale_t[1]);
-        // chunk 2
+        process(rb, mu, nb, c0 + 1, bias_t[1], scale_t[1]);
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x32(t_addr + 96, rb);
-        load_res(true, mu, nb, c0 + 3, res_b);
-        process(ra, res_a, mu, nb, c0 + 2, bias_t[CHUNKS - 2], scale_t[CHUNKS - 2]);
+        process(ra, mu, nb, c0 + 2, bias_t[CHUNKS - 2], scale_t[CHUNKS - 2]);
       } else {
-        // chunk 0 of 2
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x32(t_addr + 32, rb);
-        process(ra, res_a, mu, nb, c0, bias_t[0], scale_t[0]);
+        process(ra, mu, nb, c0, bias_t[0], scale_t[0]);
       }
       // last chunk: every TMEM read of this accumulator has completed -> hand it back to the MMA warp first
       ptx::tmem_ld_wait();
@@ -506,28 +572,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (PAIR) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
         else ptx::mbar_arrive(&tempty_bar[acc]);
       }
-      load_res(valid_n, mu_n, nb_n, c0, res_a);
-      process(rb, res_b, mu, nb, c0 + CHUNKS - 1, bias_t[CHUNKS - 1], scale_t[CHUNKS - 1]);
+      process(rb, mu, nb, c0 + CHUNKS - 1, bias_t[CHUNKS - 1], scale_t[CHUNKS - 1]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-
-      if (ln) {
-        // ---- fused LayerNorm (backbone.py:362,:373): the LN_NB CTAs holding the column tiles of these 128 rows swap
-        // per-row (sum, sum of squares) through L2, then each normalises its own tile.  The tensor core is already busy
-        // with the next tiles (the accumulator was released above), and the normalisation of tile i is deferred until
-        // tile i+1 has been drained and published, so the wait for the neighbours is never exposed.  Requires all CTAs of
-        // the grid to be co-resident (grid <= #SMs, one CTA per SM): a CTA publishes before it waits.
-        ln_publish(mu, nb);
-        if (!LN_DEFER) {
-          ln_finish(mu, nb, it & 1);
-        } else {
-          if (it > 0) ln_finish(mu_p, nb_p, (it - 1) & 1);
-          mu_p = mu;
-          nb_p = nb;
-          it_last = it;
-        }
-      }
     }
-    if (ln && LN_DEFER && it_last >= 0) ln_finish(mu_p, nb_p, it_last & 1);
   }
 
   ptx::tc_fence_before();
@@ -549,14 +596,14 @@ bool use_pair() {
   return g_pair != 0;
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, bool DEEPK>
 int launch_mode(const void* A, long long lda, const void* W, long long ldw, const GemmArgs& g, cudaStream_t st) {
   constexpr int EW = MODE == MODE_RES ? 8 : 16;
-  using C = Cfg<PAIR, EW>;
+  using C = Cfg<PAIR, EW, MODE, DEEPK>;
   constexpr int NTHREADS = C::NTHREADS;
   static bool attr_set = false;
   if (!attr_set) {
-    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<MODE, PAIR, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ma, mb;
@@ -564,6 +611,18 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&mb, W, g.N, g.K, ldw, C::B_ROWS, BK);
   if (rc) return rc;
+  CUtensorMap mres = ma, my = ma;  // only read by the residual / LayerNorm epilogue
+  if (MODE == MODE_RES) {
+    if (g.residual != nullptr) {
+      rc = make_tmap_2d_f32(&mres, g.residual, g.M, g.N, g.N, 32);
+      if (rc) return rc;
+    }
+    float* y = g.ln_gamma != nullptr ? g.ln_out_f32 : reinterpret_cast<float*>(g.out);
+    if (y != nullptr) {
+      rc = make_tmap_2d_f32(&my, y, g.M, g.N, g.ln_gamma != nullptr ? (long long)g.N : g.ldo, 32);
+      if (rc) return rc;
+    }
+  }
   const int m_units = ceil_div(g.M, C::UM), n_blocks = ceil_div(g.N, BN);
   const int work = m_units * n_blocks;
   const int max_units = PAIR ? num_sms() / 2 : num_sms();
@@ -582,9 +641,9 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW>, ma, mb, g));
+    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, ma, mb, mres, my, g));
   } else {
-    gemm_bf16_kernel<MODE, PAIR, EW><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, g);
+    gemm_bf16_kernel<MODE, PAIR, EW, DEEPK><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, mres, my, g);
   }
   prof_end(st);
   AVEXK_LAUNCH_CHECK();
@@ -593,7 +652,8 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
 
 template <int MODE>
 int launch_any(const void* A, long long lda, const void* W, long long ldw, const GemmArgs& g, cudaStream_t st) {
-  return use_pair() ? launch_mode<MODE, true>(A, lda, W, ldw, g, st) : launch_mode<MODE, false>(A, lda, W, ldw, g, st);
+  if (MODE == MODE_RES && use_pair() && g.K >= 1536) return launch_mode<MODE, true, MODE == MODE_RES>(A, lda, W, ldw, g, st);
+  return use_pair() ? launch_mode<MODE, true, false>(A, lda, W, ldw, g, st) : launch_mode<MODE, false, false>(A, lda, W, ldw, g, st);
 }
 
 }  // namespace
@@ -609,20 +669,23 @@ int gemm_bf16_launch(const void* A, long long lda, const void* W, long long ldw,
     AVEXK_CHECK_ARG(residual == nullptr, "gemm: GELU and residual epilogues are exclusive");
     return launch_any<MODE_GELU>(A, lda, W, ldw, g, st);
   }
-  if (residual != nullptr) return launch_any<MODE_RES>(A, lda, W, ldw, g, st);
+  if (residual != nullptr) {
+    AVEXK_CHECK_ARG(!out_bf16, "gemm: the residual epilogue writes fp32 (bf16 output + residual is not built)");
+    AVEXK_CHECK_ARG(N % 4 == 0 && (out == nullptr || ldo % 4 == 0), "gemm: residual epilogue needs 16-byte aligned rows");
+    return launch_any<MODE_RES>(A, lda, W, ldw, g, st);
+  }
   return launch_any<MODE_PLAIN>(A, lda, W, ldw, g, st);
 }
 
-// scratch of the fused LayerNorm epilogue: [pre-LN tile per CTA][row statistics][arrival / departure counters]
+// scratch of the fused LayerNorm epilogue: [row statistics][arrival / departure counters] (48 bytes per row)
 struct LnScratch {
   size_t tiles, stats, count, total;
 };
 LnScratch ln_scratch_layout(int M) {
   const size_t blocks = 2 * (size_t)ceil_div(M, 2 * BM);  // 128-row blocks, padded to whole CTA pairs
-  const size_t ctas = blocks * LN_NB < (size_t)num_sms() ? blocks * LN_NB + 1 : (size_t)num_sms();  // +1: pair grids are even
   LnScratch L;
   L.tiles = 0;
-  L.stats = ctas * 2 * BM * BN * sizeof(float);
+  L.stats = 0;
   L.count = L.stats + blocks * BM * 2 * LN_NB * sizeof(float2);
   L.total = L.count + ((2 * blocks * sizeof(int) + 255) & ~size_t(255));
   return L;
@@ -646,7 +709,6 @@ int gemm_bf16_ln_launch(const void* A, long long lda, const void* W, long long l
   g.M = M; g.N = LN_C; g.K = K;
   g.bias = bias; g.raw_out = raw_out; g.residual = residual; g.res_scale = res_scale;
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_out_f32 = ln_out_f32; g.ln_out_bf16 = ln_out_bf16;
-  g.ln_tiles = reinterpret_cast<float*>(base + L.tiles);
   g.ln_stats = reinterpret_cast<float2*>(base + L.stats);
   g.ln_count = reinterpret_cast<int*>(base + L.count);
   return launch_any<MODE_RES>(A, lda, W, ldw, g, st);

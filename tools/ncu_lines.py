@@ -43,7 +43,7 @@ def line_table(cubin, func_sub):
 
 def main():
     rep, cubin, sub = sys.argv[1], sys.argv[2], sys.argv[3]
-    kid = int(sys.argv[4]) if len(sys.argv) > 4 else None
+    kid = int(sys.argv[4]) if len(sys.argv) > 4 and sys.argv[4] not in ("", "-") else None
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 30
     hdr, data = sass_rows(rep, kid)
     si = hdr.index("# Samples")

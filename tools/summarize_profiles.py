@@ -3,29 +3,52 @@ import csv, json, os, subprocess, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 
+KNOWN = ("gemm_bf16_kernel", "attention_tc_kernel", "attention_gated_kernel", "posconv_kernel", "layernorm_kernel", "fbank_kernel",
+         "patchify_kernel", "group_pad_kernel", "mean_pool_kernel", "f32_to_bf16", "posconv_pack", "posconv_norm", "gate_pack",
+         "melspec", "dwconv_kernel", "se_mlp_kernel", "se_apply_kernel", "stem_kernel")
+
+
 def launches(csv_path, out_name):
+    """Per-kernel launch list: count, device time and share; DRAM bytes per launch when the capture holds them
+    (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum)."""
     rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
     hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     h = rows[hdr_i]
-    kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
-    agg = collections.OrderedDict()
-    total = 0.0
+    kn, mn, mv, mu, idc = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit"), h.index("ID")
+    per = collections.OrderedDict()  # launch id -> {name, ms, rd, wr}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows[hdr_i + 1:]:
         v = float(r[mv].replace(",", ""))
         unit = r[mu]
-        ms = v / 1e6 if unit.startswith("ns") else v / 1e3 if unit.startswith("us") else v if unit.startswith("ms") else v * 1e3
         name = r[kn].split("(")[0]
-        for k in ("gemm_bf16_kernel", "attention_gated_kernel", "posconv_kernel", "layernorm_kernel", "fbank_kernel", "patchify_kernel",
-                  "group_pad_kernel", "mean_pool_kernel", "f32_to_bf16", "posconv_pack", "posconv_norm", "gate_pack"):
+        for k in KNOWN:
             if k in name:
                 name = k
-        a = agg.setdefault(name, [0, 0.0])
-        a[0] += 1; a[1] += ms; total += ms
-    lines = [f"# ncu --metrics gpu__time_duration.sum --clock-control none  (cold-cache, serialised: compare SHARES)", f"# source: {os.path.basename(csv_path)}; total {total:.3f} ms over {sum(a[0] for a in agg.values())} launches", "kernel,launches,total_ms,share"]
-    for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        lines.append(f"{k},{n},{ms:.4f},{ms / total:.4f}")
+        # template arguments distinguish the GEMM epilogues: keep mode / pair / warps
+        if name == "gemm_bf16_kernel" and "<" in r[kn]:
+            name += "<" + r[kn].split("<", 2)[-1].split(">")[0].replace("(int)", "").replace("(bool)", "") + ">"
+        e = per.setdefault(r[idc], {"name": name, "ms": 0.0, "rd": None, "wr": None})
+        if r[mn].startswith("gpu__time_duration"):
+            e["ms"] = v / 1e6 if unit.startswith("ns") else v / 1e3 if unit.startswith("us") else v if unit.startswith("ms") else v * 1e3
+        elif r[mn].startswith("dram__bytes_read"):
+            e["rd"] = v * scale.get(unit, 1.0)
+        elif r[mn].startswith("dram__bytes_write"):
+            e["wr"] = v * scale.get(unit, 1.0)
+    agg = collections.OrderedDict()
+    total = 0.0
+    for e in per.values():
+        a = agg.setdefault(e["name"], [0, 0.0, 0.0, 0.0, False])
+        a[0] += 1; a[1] += e["ms"]; total += e["ms"]
+        if e["rd"] is not None:
+            a[2] += e["rd"]; a[3] += e["wr"] or 0.0; a[4] = True
+    lines = ["# ncu --clock-control none launch list (cold-cache, serialised: compare SHARES, not absolutes)",
+             f"# source: {os.path.basename(csv_path)}; total {total:.3f} ms over {len(per)} launches",
+             "kernel,launches,total_ms,share,avg_ms,avg_dram_read_MB,avg_dram_write_MB"]
+    for k, (n, ms, rd, wr, has) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"{k},{n},{ms:.4f},{ms / total:.4f},{ms / n:.4f}," + (f"{rd / n / 1e6:.2f},{wr / n / 1e6:.2f}" if has else ","))
     open(os.path.join(OUT, out_name), "w").write("\n".join(lines) + "\n")
-    print("\n".join(lines[:12]))
+    print("\n".join(lines[:16]))
+
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
