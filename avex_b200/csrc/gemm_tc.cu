@@ -52,14 +52,19 @@ struct Cfg {
   // EW = 8: 384 x 168 = 64512 >= 128*64 + 256*216 = 63488;  EW = 16: 640 x 96 = 61440 >= 128*56 + 512*104 = 60416
   static constexpr int CTRL_REGS = EW == 8 ? 64 : 56, EPI_REGS = EW == 8 ? 216 : 104;
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of W each CTA stages per k-block
-  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  // a pipeline stage holds KSUB k-blocks of 64 (one 128-byte swizzle atom wide each): fewer barrier round trips per MMA
+  // (measured: qkv 1262 -> 1276, fc1+GELU 1216 -> 1291 TFLOP/s; with only two such stages fc2 lost 7 %, so MODE_RES keeps KSUB = 1)
+  static constexpr int KSUB = (MODE == MODE_PLAIN || MODE == MODE_GELU) ? 2 : 1;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2, SUB_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = KSUB * SUB_BYTES;
   // MODE_RES spends 96 KB of shared memory on the residual ring, so it keeps fewer operand stages
   static constexpr int RES_DEPTH = (PAIR && DEEPK) ? 2 : 3;  // residual boxes in flight per epilogue warp (MODE_RES)
-  static constexpr int STAGES = MODE == MODE_RES ? (PAIR ? (DEEPK ? 4 : 3) : 2) : (PAIR ? (EW == 8 ? 6 : 5) : (EW == 8 ? 4 : 3));
-  static constexpr int TX_BYTES = STAGE_BYTES * (PAIR ? 2 : 1);  // bytes landing on the (leader's) full barrier
+  // per-warp output staging: 32 rows x 64 bytes for the bias / GELU epilogue, 32 x 128 bytes for the others
+  static constexpr int STG_BYTES = (MODE == MODE_PLAIN || MODE == MODE_GELU) ? STG_BYTES_PER_WARP / 2 : STG_BYTES_PER_WARP;
+  static constexpr int STAGES = MODE == MODE_RES ? (PAIR ? (DEEPK ? 4 : 3) : 2) : MODE == MODE_CONV ? (PAIR ? 5 : 3) : (PAIR ? 3 : 2);
+  static constexpr int TX_SUB = SUB_BYTES * (PAIR ? 2 : 1);  // bytes landing on the (leader's) full barrier per k-block
   static constexpr int UM = PAIR ? 2 * BM : BM;                  // output rows per scheduling unit
   static constexpr int RES_BYTES = MODE == MODE_RES ? EW * RES_DEPTH * STG_BYTES_PER_WARP : 0;
-  static constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_RES = OFF_STG + EW * STG_BYTES_PER_WARP, OFF_BAR = OFF_RES + RES_BYTES;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES, OFF_RES = OFF_STG + EW * STG_BYTES, OFF_BAR = OFF_RES + RES_BYTES;
   static constexpr int SMEM_BYTES = 1024 + OFF_BAR + 512;
   static_assert(SMEM_BYTES <= 232448, "gemm: shared memory budget");
 };
@@ -172,10 +177,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
-    if (MODE == MODE_RES) {
-      ptx::prefetch_tensormap(&map_res);
-      ptx::prefetch_tensormap(&map_y);
-    }
+    if (MODE == MODE_RES) ptx::prefetch_tensormap(&map_res);
+    if (MODE != MODE_CONV) ptx::prefetch_tensormap(&map_y);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -216,17 +219,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (!tile_of(it, mu, nb)) break;
           const int m0 = mu * C::UM + static_cast<int>(rank) * BM;
           const int n0 = nb * BN + static_cast<int>(rank) * C::B_ROWS;
-          for (int kb = 0; kb < num_kb; ++kb) {
+          for (int kb = 0; kb < num_kb; kb += C::KSUB) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            unsigned char* sa = stage_base + stage * C::STAGE_BYTES;
-            if (PAIR) {
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
-              ptx::tma_load_2d_pair(sa, &map_a, full0 + stage * 8, kb * BK, m0);
-              ptx::tma_load_2d_pair(sa + C::A_BYTES, &map_b, full0 + stage * 8, kb * BK, n0);
-            } else {
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], C::TX_BYTES);
-              ptx::tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, m0);
-              ptx::tma_load_2d(sa + C::A_BYTES, &map_b, &full_bar[stage], kb * BK, n0);
+            const int nsub = num_kb - kb < C::KSUB ? num_kb - kb : C::KSUB;
+            if (!PAIR || rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], nsub * C::TX_SUB);
+#pragma unroll
+            for (int sb = 0; sb < C::KSUB; ++sb) {
+              if (sb >= nsub) break;
+              unsigned char* sa = stage_base + stage * C::STAGE_BYTES + sb * C::SUB_BYTES;
+              if (PAIR) {
+                ptx::tma_load_2d_pair(sa, &map_a, full0 + stage * 8, (kb + sb) * BK, m0);
+                ptx::tma_load_2d_pair(sa + C::A_BYTES, &map_b, full0 + stage * 8, (kb + sb) * BK, n0);
+              } else {
+                ptx::tma_load_2d(sa, &map_a, &full_bar[stage], (kb + sb) * BK, m0);
+                ptx::tma_load_2d(sa + C::A_BYTES, &map_b, &full_bar[stage], (kb + sb) * BK, n0);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -250,23 +257,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; kb += C::KSUB) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           if (lane == 0) {
-            const uint32_t sa = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
-            const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sa + C::A_BYTES);
+            const int nsub = num_kb - kb < C::KSUB ? num_kb - kb : C::KSUB;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-              if (PAIR) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int sb = 0; sb < C::KSUB; ++sb) {
+              if (sb >= nsub) break;
+              const uint32_t sa = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES + sb * C::SUB_BYTES);
+              const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+                if (PAIR) ptx::umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | sb | k) != 0 ? 1u : 0u);
+                else ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | sb | k) != 0 ? 1u : 0u);
+              }
             }
+            const bool last = kb + C::KSUB >= num_kb;
             if (PAIR) {
-              ptx::umma_commit_pair(&empty_bar[stage], 3);                      // both CTAs' smem slots are free
-              if (kb == num_kb - 1) ptx::umma_commit_pair(&tfull_bar[acc], 3);  // both halves of the accumulator complete
+              ptx::umma_commit_pair(&empty_bar[stage], 3);              // both CTAs' smem slots are free
+              if (last) ptx::umma_commit_pair(&tfull_bar[acc], 3);      // both halves of the accumulator complete
             } else {
               ptx::umma_commit(&empty_bar[stage]);
-              if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[acc]);
+              if (last) ptx::umma_commit(&tfull_bar[acc]);
             }
           }
           __syncwarp();
@@ -464,13 +477,114 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) ptx::tma_store_wait_all();  // the bulk stores must have been performed before the CTA exits
+  } else if constexpr (MODE != MODE_CONV) {
+    // ===================== bias / GELU epilogue (warps 4..19): lane = output row =====================
+    // Warp (quarter q, group h) owns rows 32q..32q+31 and the 64 columns 64h..64h+63 of every tile.  Both 32-column TMEM
+    // chunks are read up front, so the accumulator goes back to the MMA warp before any arithmetic; the finished 32x64
+    // bf16 box (or two 32x32 fp32 boxes) is staged in 128-byte-swizzled shared memory and written by TMA: no transposition,
+    // no per-element address arithmetic, full 128-byte lines on the way out.
+    ptx::setmaxnreg_inc<C::EPI_REGS>();
+    static_assert(CHUNKS == 2, "the bias / GELU epilogue is written for 16 warps");
+    const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;
+    const uint32_t ybuf = ptx::smem_u32(stg_base) + ew * C::STG_BYTES;  // 32 rows x 64 bytes, 64-byte swizzle
+    const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
+    const uint32_t rowoff = lane * 64, sw = (lane >> 1) & 3;  // 16-byte chunk j of row r is stored at chunk j ^ ((r >> 1) & 3)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    // hand a staged 32-row x 64-byte box to the TMA engine (rows >= M / columns >= N are clipped by the tensor map)
+    auto flush_box = [&](int col, int row) {
+      ptx::fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d_s(&map_y, ybuf, col, row);
+        ptx::tma_store_commit();
+      }
+    };
+    auto claim_box = [&]() {  // the previous box has left the staging buffer
+      if (lane == 0) ptx::tma_store_wait_read();
+      __syncwarp();
+    };
+    for (int it = 0;; ++it) {
+      int mu, nb;
+      if (!tile_of(it, mu, nb)) break;
+      const int row0 = mu * C::UM + static_cast<int>(rank) * BM + quarter * 32, grow = row0 + lane;
+      const int colb = nb * BN + half * 64;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 64;
+      uint32_t r[2][32];
+      ptx::tmem_ld_32x32(t_addr, r[0]);
+      ptx::tmem_ld_32x32(t_addr + 32, r[1]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
+        else ptx::mbar_arrive(&tempty_bar[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = colb + c * 32;
+        if (col0 >= g.N) continue;  // warp-uniform (N tail)
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias != nullptr && col0 + 4 * j < g.N) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + col0) + j);  // warp-uniform
+          v[4 * j] = __uint_as_float(r[c][4 * j]) + b4.x;
+          v[4 * j + 1] = __uint_as_float(r[c][4 * j + 1]) + b4.y;
+          v[4 * j + 2] = __uint_as_float(r[c][4 * j + 2]) + b4.z;
+          v[4 * j + 3] = __uint_as_float(r[c][4 * j + 3]) + b4.w;
+        }
+        if (MODE == MODE_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 gl = gelu_fast2(make_float2(v[2 * j], v[2 * j + 1]));
+            v[2 * j] = gl.x;
+            v[2 * j + 1] = gl.y;
+          }
+        }
+        if (g.raw_out != nullptr && grow < g.M) {  // hook on the Linear: rare, plain per-row stores
+          float4* dst = reinterpret_cast<float4*>(g.raw_out + (size_t)grow * g.N + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col0 + 4 * j < g.N) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (g.out == nullptr) continue;
+        if (g.out_bf16) {  // one 32 x 32 bf16 box
+          claim_box();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = ybuf + rowoff + ((j ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(v[8 * j], v[8 * j + 1])),
+                         "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])),
+                         "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7]))
+                         : "memory");
+          }
+          flush_box(col0, row0);
+        } else {  // two 32 x 16 fp32 boxes
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (col0 + 16 * h2 >= g.N) continue;
+            claim_box();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128f(ybuf + rowoff + ((j ^ sw) << 4), v[16 * h2 + 4 * j], v[16 * h2 + 4 * j + 1], v[16 * h2 + 4 * j + 2], v[16 * h2 + 4 * j + 3]);
+            flush_box(col0 + 16 * h2, row0);
+          }
+        }
+      }
+    }
+    if (lane == 0) ptx::tma_store_wait_all();  // the bulk stores must have been performed before the CTA exits
   } else {
-    // ===================== bias / GELU / conv epilogue (warps 4..19) =====================
+    // ===================== conv epilogue (warps 4..19) =====================
     // Four warps per TMEM lane quarter; each owns CHUNKS of the tile's eight 32-column chunks.  The TMEM load of the next
     // chunk is in flight while the current one is transposed through shared memory and stored with 16-byte coalesced writes.
     ptx::setmaxnreg_inc<C::EPI_REGS>();
     const int ew = warp - CTRL_WARPS, quarter = warp & 3, half = ew >> 2;  // half: which group of CHUNKS chunks
     float* stg = stg_base + ew * (32 * 32);
+    static_assert(MODE != MODE_CONV || C::STG_BYTES == STG_BYTES_PER_WARP, "conv epilogue staging");
     const int rsub = lane >> 3, csub = lane & 7;  // row-in-group-of-4, 16-byte column slot inside a 128-byte row segment
     const uint32_t tempty0 = PAIR ? ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0) : 0u;
     int acc = 0;
@@ -611,7 +725,11 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&mb, W, g.N, g.K, ldw, C::B_ROWS, BK);
   if (rc) return rc;
-  CUtensorMap mres = ma, my = ma;  // only read by the residual / LayerNorm epilogue
+  CUtensorMap mres = ma, my = ma;  // mres: residual / LayerNorm epilogue; my: output of every epilogue but the conv one
+  if ((MODE == MODE_PLAIN || MODE == MODE_GELU) && g.out != nullptr) {
+    rc = make_tmap_2d_64B(&my, g.out, g.M, g.N, g.ldo, g.out_bf16 ? 2 : 4, 32);
+    if (rc) return rc;
+  }
   if (MODE == MODE_RES) {
     if (g.residual != nullptr) {
       rc = make_tmap_2d_f32(&mres, g.residual, g.M, g.N, g.N, 32);

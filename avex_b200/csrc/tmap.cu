@@ -64,6 +64,29 @@ int make_tmap_2d_f32(CUtensorMap* map, const void* base, long long rows, long lo
   return AVEXK_OK;
 }
 
+int make_tmap_2d_64B(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int elem_bytes, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return AVEXK_ECUDA;
+  }
+  AVEXK_CHECK_ARG(elem_bytes == 2 || elem_bytes == 4, "bad element size %d", elem_bytes);
+  AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * elem_bytes) % 16 == 0, "TMA operand must be 16-byte aligned (ld=%lld)", ld);
+  AVEXK_CHECK_ARG(box_rows >= 1 && box_rows <= 256, "bad TMA box rows %d", box_rows);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(64 / elem_bytes), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(2d 64B) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld);
+    return AVEXK_ECUDA;
+  }
+  return AVEXK_OK;
+}
+
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long ld1,
                       long long ld2, int b0, int b1, int b2, bool swizzle128) {
   EncodeTiledFn enc = get_encode();

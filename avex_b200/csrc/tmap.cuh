@@ -12,6 +12,8 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, long long rows, long l
                       int box_cols);
 // fp32 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 32] (128-byte rows, 128-byte swizzle).
 int make_tmap_2d_f32(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
+// row-major [rows, cols] of 2-byte (bf16) or 4-byte (fp32) elements; box = [box_rows, 64 bytes] with 64-byte swizzle.
+int make_tmap_2d_64B(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int elem_bytes, int box_rows);
 // bf16 [d2, d1, d0] (d0 innermost) with pitches ld1 (elements between d1 steps) and ld2; box [b2, b1, b0].
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long ld1,
                       long long ld2, int b0, int b1, int b2, bool swizzle128);

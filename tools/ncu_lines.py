@@ -21,7 +21,7 @@ def sass_rows(rep, kid):
 
 
 def line_table(cubin, func_sub):
-    out = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    out = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
     table, cur, active = {}, None, False
     for ln in out.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+)", ln)
@@ -30,10 +30,12 @@ def line_table(cubin, func_sub):
             continue
         if not active:
             continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
-        if m:
-            inl = "inlined" in ln
-            cur = (m.group(1).split("/")[-1], int(m.group(2)), inl)
+        if "//## File" in ln:
+            # attribute inlined helpers (ptx.cuh wrappers ...) to their outermost call site
+            ms = re.findall(r'"([^"]+)", line (\d+)', ln)
+            if ms:
+                f, l = ms[-1]
+                cur = (f.split("/")[-1], int(l), len(ms) > 1)
             continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
         if m and cur:
