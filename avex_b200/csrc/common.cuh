@@ -63,6 +63,23 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
+// Exact (erf) GELU for two values with packed fp32x2 arithmetic and one special-function op per value:
+// gelu(v) = relu(v) - |v| * (erfc(|v| / sqrt2) / 2) with log2(erfc(|v| / sqrt2) / 2) as a degree-5 polynomial (|err| <= 6.5e-7
+// over the real line; derivation in gemm_tc.cu).
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 v) {
+  const float2 n = make_float2(-fabsf(v.x), -fabsf(v.y));
+  const float2 r = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+  float2 q = __ffma2_rn(make_float2(4.712853462e-4f, 4.712853462e-4f), n, make_float2(7.064215249e-3f, 7.064215249e-3f));
+  q = __ffma2_rn(q, n, make_float2(5.175841926e-2f, 5.175841926e-2f));
+  q = __ffma2_rn(q, n, make_float2(-4.600918231e-1f, -4.600918231e-1f));
+  q = __ffma2_rn(q, n, make_float2(1.150727814f, 1.150727814f));
+  q = __ffma2_rn(q, n, make_float2(-1.000049354f, -1.000049354f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  return __ffma2_rn(n, e, r);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -185,15 +185,17 @@ __global__ void posconv_norm_kernel(const float* __restrict__ v, int CoCi, int K
   if (threadIdx.x == 0) nrm[t] = (float)sqrt(sh[0]);
 }
 
-// Wpc [C, K*64] bf16: Wpc[co, t*64 + ci] = g[t] * v[co, ci, t] / nrm[t] for ci < cg, 0 for the pad channels.
+// Wpc [G][K][cg][64] bf16: Wpc[grp, t, co, ci] = g[t] * v[grp*cg + co, ci, t] / nrm[t] for ci < cg, 0 for the pad channels
+// (consecutive taps of one group are consecutive 128-byte rows: the pos-conv kernel fetches four taps per TMA box).
 __global__ void posconv_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ nrm,
                                     int C, int cg, int K, __nv_bfloat16* __restrict__ W) {
   const long long total = (long long)C * K * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ci = i & 63, t = (i >> 6) % K;
-    const int co = i / (64LL * K);
+    const int ci = i & 63;
+    const long long q = i >> 6;  // (grp, t, co)
+    const int co = q % cg, t = (q / cg) % K, grp = q / ((long long)cg * K);
     float w = 0.f;
-    if (ci < cg) w = g[t] * v[((size_t)co * cg + ci) * K + t] / nrm[t];
+    if (ci < cg) w = g[t] * v[((size_t)(grp * cg + co) * cg + ci) * K + t] / nrm[t];
     W[i] = __float2bfloat16_rn(w);
   }
 }
