@@ -43,6 +43,27 @@ def peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
+def gemm_traffic_from_profile():
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum), averaged over the GEMM
+    launches of one bench step, from the committed ncu launch list of this same command (profiles/launches_*.csv)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "launches_r*.csv")))
+    if not files:
+        return None, None
+    n_tot, bytes_tot = 0, 0.0
+    for ln in open(files[-1]):
+        if ln.startswith("gemm_bf16_kernel"):
+            f = ln.rstrip("\n").rsplit(",", 6)
+            try:
+                n, rd, wr = int(f[1]), float(f[5]), float(f[6])
+            except (ValueError, IndexError):
+                continue
+            n_tot += n
+            bytes_tot += n * (rd + wr) * 1e6
+    return (bytes_tot / n_tot, os.path.basename(files[-1])) if n_tot else (None, None)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # CPU baseline: the numpy oracle port (oracle/), all host threads (OpenBLAS), bounded sample
 # ------------------------------------------------------------------------------------------------------------
@@ -289,6 +310,13 @@ def run_ours(args):
             "frac": tf / pk["tf_sustained"], "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
             "traffic": None, "launches_per_step": gm["launches"], "avg_launch_ms": gm["ms_per_step"] / max(1, gm["launches"]),
             "share_of_step": gm["ms_per_step"] / ms_per_step}  # fmt: skip
+    traffic, src = gemm_traffic_from_profile()
+    if traffic is not None:
+        roof["traffic"] = traffic
+        roof["traffic_source"] = f"profiles/{src}: mean dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (ncu, same command)"
+        # algorithmic HBM bytes per launch for comparison: operands read once, outputs written once (per-step totals / launches)
+        roof["algorithmic_bytes_per_launch"] = B * 496 * (12 * (768 * 2 + 2304 * 2) + 12 * (768 * 2 + 768 * 4 + 768 * 6) + 12 * (768 * 2 + 3072 * 2)
+                                                          + 12 * (3072 * 2 + 768 * 4 + 768 * 6) + (768 * 2 + 512 * 4) + (1536 * 2 + 768 * 4)) / max(1, gm["launches"])
     fbk = prof["fbank"]
     fb_gbs = fbk["work_per_step"] / (fbk["ms_per_step"] * 1e-3) / 1e9 if fbk["ms_per_step"] > 0 else 0.0
     kernels = {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches": v["launches"]} for k, v in prof.items()}
@@ -331,6 +359,127 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# secondary workload: EfficientNet-B0 mel-spectrogram feature extractor (BASELINE configs[2])
+# ------------------------------------------------------------------------------------------------------------
+EFF_CLIP_SECONDS = 5
+EFF_ACT_BYTES_PER_CLIP = 35.0e6      # ~35 MB of bf16 activation traffic per 5 s clip (unfused NHWC path)
+EFF_MEL_BYTES_PER_CLIP = 4 * 80000 + 4 * 128 * 501  # waveform in, single-channel log-mel out
+
+
+def run_effnet(args):
+    """`--workload effnet`: 5 s clips -> mel -> EfficientNet-B0 features [B,1280,4,16] through the plugin Model.  Prints one
+    JSON line of the same shape as the main workload (metric effnet_b0_feature_throughput, clips/s)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from avex_b200 import _lib, plugin
+    from avex_b200.plugin import efficientnet_model  # noqa: F401
+    from oracle.weights import make_effnet_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; avex_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    spec = plugin.ModelSpec(name="efficientnet", device="cuda", efficientnet_variant="b0",
+                            audio_config=dict(sample_rate=16000, n_fft=800, hop_length=160, win_length=800, window="hann", n_mels=128,
+                                              representation="mel_spectrogram", normalize=True, target_length_seconds=10,
+                                              window_selection="random"))  # fmt: skip
+    plugin.register_model("bench_effnet_b0", spec)
+    model = plugin.build_model_from_spec(spec, "cuda", pretrained=False, return_features_only=True).eval()
+    stats_path = os.path.join(ROOT, "tests", "golden", "effnet_bn_stats.npz")
+    W = make_effnet_weights(seed=3, num_classes=0, bn_stats=dict(np.load(stats_path)))  # calibrated BatchNorm statistics
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in W.items()}, strict=False)
+    B = args.batch if args.batch != BATCH_PER_GPU else 512 // max(1, world) if world > 1 else 512
+    T = EFF_CLIP_SECONDS * SAMPLE_RATE
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    wav_dev = torch.randn(B, T, device=dev, generator=g) * 0.1
+    host = torch.empty(B, T, dtype=torch.float32).pin_memory()
+    host.copy_(wav_dev.cpu())
+    feat_host = torch.empty(B, 1280, dtype=torch.float32).pin_memory()
+
+    def step_device(_i=0):
+        with torch.no_grad():
+            return model(wav_dev)
+
+    def step_e2e(_i=0):
+        x = host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            f = model(x)
+        feat_host.copy_(f.mean(dim=(2, 3)), non_blocking=True)
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    W_, K_ = max(3, args.warmup), args.steps
+    for _ in range(W_):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = _lib.launch_count()
+    ms = timed(step_device, K_) / K_
+    launches = _lib.launch_count() - l0
+    ms_e2e = timed(step_e2e, K_) / K_
+    mel = model._engine.mel
+    ms_mel = timed(lambda i: mel.run(wav_dev, normalize=True), K_) / K_
+    if rank == 0:
+        sampler.stop()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    clips_per_s = world * B / (ms * 1e-3)
+    act_gbs = B * EFF_ACT_BYTES_PER_CLIP / (ms * 1e-3) / 1e9
+    mel_gbs = B * EFF_MEL_BYTES_PER_CLIP / (ms_mel * 1e-3) / 1e9
+    line = {
+        "metric": "effnet_b0_feature_throughput", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": K_, "warmup": W_,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "EfficientNet-B0 mel-spectrogram feature extractor, 512 x 5 s clips @16 kHz (BASELINE configs[2]), features [B,1280,4,16]",
+                   "batch_per_gpu": B, "global_batch": world * B, "clip_seconds": EFF_CLIP_SECONDS, "weights": "random-init, calibrated BatchNorm statistics",
+                   "audio_hours_per_s": clips_per_s * EFF_CLIP_SECONDS / 3600.0,
+                   "l2": "activations (up to 1.6 GB per layer) exceed the 126 MB L2; no flush needed"},
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": world * B * T * 4, "d2h_bytes_per_step": world * B * 1280 * 4,
+                "ms_per_step": ms_e2e, "api": "plugin Model.forward with pinned host input; pooled [B,1280] features read back"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "whole forward (NHWC bf16 activations)", "achieved": act_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": act_gbs / pk["hbm_gbs"], "peak_source": f"{pk['src']} hbm_gbs", "traffic": None,
+                     "algorithmic_bytes": "35 MB of bf16 activation traffic per 5 s clip (SURVEY 8d)"},
+        "kernels": {"melspec": {"ms_per_step": round(ms_mel, 4), "achieved_GBps": mel_gbs, "hbm_frac": mel_gbs / pk["hbm_gbs"],
+                                "algorithmic_bytes_per_clip": EFF_MEL_BYTES_PER_CLIP}},
+        "cpu_baseline": None,
+        "clocks": sampler.summary(),
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,8 +488,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="beats", choices=["beats", "effnet"],
+                    help="beats (default): the BASELINE.json metric; effnet: secondary line for the EfficientNet-B0 path")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "effnet" and args.impl == "ours":
+        run_effnet(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
