@@ -198,6 +198,9 @@ class BEATs(nn.Module):
         self.predictor = nn.Linear(cfg.encoder_embed_dim, cfg.predictor_class) if cfg.finetuned_model else None
         self._engine = None
         self._engine_key = None
+        # "bf16" (default): bf16 tensor-core operands, max-abs <= 2e-2 vs the fp32 reference.  "fp32": 3-term split GEMMs with
+        # fp32 attention / pos-conv (max-abs <= 1e-3; ~10x slower) -- set `model.backbone.precision = "fp32"` before a forward.
+        self.precision = "bf16"
         self._bias_cache: dict = {}
         self._ws: Optional[torch.Tensor] = None
 
@@ -206,7 +209,7 @@ class BEATs(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _ensure_engine(self, device: torch.device):
-        key = (device, self._weight_version())
+        key = (device, self._weight_version(), self.precision)
         if self._engine is not None and self._engine_key == key:
             return self._engine
         lib = _lib.load()
@@ -228,6 +231,7 @@ class BEATs(nn.Module):
 
         with torch.cuda.device(device):
             _lib.check(lib.avexk_beats_create(C.byref(dims), C.byref(h)), "avexk_beats_create")
+            _lib.check(lib.avexk_beats_set_precision(h, 1 if self.precision == "fp32" else 0), "avexk_beats_set_precision")
             enc = self.encoder
             layers = (_lib.BeatsLayerWeights * cfg.encoder_layers)()
             for i, blk in enumerate(enc.layers):

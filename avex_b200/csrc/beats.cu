@@ -22,8 +22,11 @@ struct avexk_beats {
   // packed weights (device)
   __nv_bfloat16 *patch_w = nullptr, *proj_w = nullptr, *posconv_w = nullptr;
   float *ln0_w, *ln0_b, *proj_b, *posconv_b, *enc_ln_w, *enc_ln_b;
+  int precision = 0;  // 0: bf16 operands (default); 1: fp32 mode (3-term split GEMMs, fp32 attention and pos-conv)
+  float* posconv_wf = nullptr;
   struct Layer {
     __nv_bfloat16 *qkv_w, *o_w, *fc1_w, *fc2_w;
+    __nv_bfloat16 *qkv_w3 = nullptr, *o_w3 = nullptr, *fc1_w3 = nullptr, *fc2_w3 = nullptr;  // [hi|hi|lo] rows, fp32 mode
     float *qkv_b, *o_b, *fc1_b, *fc2_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b, *gate_w, *gate_b, *grep_a;
   };
   std::vector<Layer> layers;
@@ -78,7 +81,7 @@ struct Plan {
   long long M;
 };
 
-size_t workspace_bytes(const avexk_beats_dims& d, int B, int T) {
+size_t workspace_bytes(const avexk_beats_dims& d, int B, int T, int precision = 0) {
   const long long F = avexk_fbank_num_frames(T), N = 8 * (F / 16), M = (long long)B * N;
   const long long C = d.embed, E = d.patch_embed, Ff = d.ffn, G = d.conv_groups;
   auto al = [](long long b) { return (size_t)((b + 255) & ~255LL); };
@@ -96,6 +99,14 @@ size_t workspace_bytes(const avexk_beats_dims& d, int B, int T) {
   s += al(M * Ff * 2);                  // h
   s += al(M * C * 4);                   // tmp: pre-LN sums (pos-conv; GEMM epilogues when the LayerNorm is not fused)
   s += al((long long)gemm_ln_scratch_bytes((int)M));  // fused GEMM+LayerNorm: per-CTA tiles, row statistics, counters
+  if (precision == 1) {
+    s += al(M * 3 * C * 2);   // xs   [hi|lo|hi] of x
+    s += al(M * 3 * C * 4);   // qkv  fp32
+    s += al(M * C * 4);       // att  fp32
+    s += al(M * 3 * C * 2);   // atts [hi|lo|hi] of att
+    s += al(M * Ff * 4);      // h    fp32
+    s += al(M * 3 * Ff * 2);  // hs   [hi|lo|hi] of h
+  }
   return s + 4096;
 }
 
@@ -151,6 +162,10 @@ extern "C" int avexk_beats_load_weights(avexk_beats_t* h, const avexk_beats_weig
   TRY(dev_alloc(h, &nrm, K));
   TRY(dev_alloc(h, &h->posconv_w, C * K * 64));
   TRY(launch_posconv_pack(w->posconv_v, w->posconv_g, (int)C, (int)cg, (int)K, nrm, h->posconv_w, st));
+  if (h->precision == 1) {
+    TRY(dev_alloc(h, &h->posconv_wf, C * cg * K));
+    TRY(launch_posconv_pack_f32(w->posconv_v, w->posconv_g, nrm, (int)G, (int)cg, (int)K, h->posconv_wf, st));
+  }
   for (int li = 0; li < d.layers; ++li) {
     const avexk_beats_layer_weights& s = w->layers[li];
     avexk_beats::Layer& L = h->layers[li];
@@ -168,6 +183,18 @@ extern "C" int avexk_beats_load_weights(avexk_beats_t* h, const avexk_beats_weig
     TRY(copy_f32(h, &L.fc1_b, s.fc1_b, Ff, st));
     TRY(pack_bf16_w(h, &L.fc2_w, s.fc2_w, C * Ff, st));
     TRY(copy_f32(h, &L.fc2_b, s.fc2_b, C, st));
+    if (h->precision == 1) {
+      TRY(dev_alloc(h, &L.qkv_w3, 3 * C * 3 * C));
+      TRY(launch_f32_to_bf16_split3(s.q_w, L.qkv_w3, (int)C, (int)C, st));
+      TRY(launch_f32_to_bf16_split3(s.k_w, L.qkv_w3 + C * 3 * C, (int)C, (int)C, st));
+      TRY(launch_f32_to_bf16_split3(s.v_w, L.qkv_w3 + 2 * C * 3 * C, (int)C, (int)C, st));
+      TRY(dev_alloc(h, &L.o_w3, C * 3 * C));
+      TRY(launch_f32_to_bf16_split3(s.o_w, L.o_w3, (int)C, (int)C, st));
+      TRY(dev_alloc(h, &L.fc1_w3, Ff * 3 * C));
+      TRY(launch_f32_to_bf16_split3(s.fc1_w, L.fc1_w3, (int)Ff, (int)C, st));
+      TRY(dev_alloc(h, &L.fc2_w3, C * 3 * Ff));
+      TRY(launch_f32_to_bf16_split3(s.fc2_w, L.fc2_w3, (int)C, (int)Ff, st));
+    }
     TRY(copy_f32(h, &L.ln1_w, s.ln1_w, C, st));
     TRY(copy_f32(h, &L.ln1_b, s.ln1_b, C, st));
     TRY(copy_f32(h, &L.ln2_w, s.ln2_w, C, st));
@@ -185,7 +212,17 @@ extern "C" int avexk_beats_load_weights(avexk_beats_t* h, const avexk_beats_weig
 
 extern "C" size_t avexk_beats_workspace_bytes(const avexk_beats_t* h, int B, int T) {
   if (!h || B <= 0 || T < 400) return 0;
-  return avexk::workspace_bytes(h->d, B, T);
+  return avexk::workspace_bytes(h->d, B, T, h->precision);
+}
+
+extern "C" int avexk_beats_set_precision(avexk_beats_t* h, int fp32_mode) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(h && (fp32_mode == 0 || fp32_mode == 1), "avexk_beats_set_precision: bad argument");
+  if (h->precision != fp32_mode) {
+    h->precision = fp32_mode;
+    h->loaded = false;  // the split weight copies are packed by avexk_beats_load_weights
+  }
+  return AVEXK_OK;
 }
 
 extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, int T, long long wav_stride,
@@ -201,7 +238,7 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   AVEXK_CHECK_ARG(B > 0 && N > 0, "avexk_beats_forward: clip too short (B=%d T=%d -> %d tokens)", B, T, N);
   const long long M = (long long)B * N;
   AVEXK_CHECK_ARG(M < (1LL << 31), "avexk_beats_forward: too many token rows (%lld)", M);
-  AVEXK_CHECK_ARG(workspace_bytes >= avexk::workspace_bytes(d, B, T), "avexk_beats_forward: workspace too small");
+  AVEXK_CHECK_ARG(workspace_bytes >= avexk::workspace_bytes(d, B, T, h->precision), "avexk_beats_forward: workspace too small");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int C = d.embed, E = d.patch_embed, Ff = d.ffn, G = d.conv_groups, H = d.heads;
   const float alpha = powf(2.0f * (float)d.layers, 0.25f);  // backbone.py:306
@@ -257,8 +294,43 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   TRY(gemm(peb, 3 * E, h->proj_w, C, h->proj_b, 0, nullptr, nullptr, 0.f, x0, 0));
   // ---- encoder prologue: mask, pos-conv + GELU + residual, LN (backbone.py:169-177) ------------------------------
   TRY(launch_group_pad(x0, key_pad, M, G, C / G, xg, st));
-  TRY(launch_posconv(xg, h->posconv_w, h->posconv_b, x0, tmp, B, N, G, C / G, d.conv_pos, st));
-  TRY(launch_layernorm(tmp, (int)M, C, h->enc_ln_w, h->enc_ln_b, d.ln_eps, x, xb, st));
+  if (h->precision != 1) {
+    TRY(launch_posconv(xg, h->posconv_w, h->posconv_b, x0, tmp, B, N, G, C / G, d.conv_pos, st));
+    TRY(launch_layernorm(tmp, (int)M, C, h->enc_ln_w, h->enc_ln_b, d.ln_eps, x, xb, st));
+  }
+  if (h->precision == 1) {
+    // ---- fp32 mode: 3-term split-bf16 GEMMs (K tripled), fp32 attention / pos-conv / residual stream ----------------------
+    __nv_bfloat16* xs = cw.take<__nv_bfloat16>((size_t)M * 3 * C);
+    float* qkv32 = cw.take<float>((size_t)M * 3 * C);
+    float* att32 = cw.take<float>((size_t)M * C);
+    __nv_bfloat16* atts = cw.take<__nv_bfloat16>((size_t)M * 3 * C);
+    float* h32 = cw.take<float>((size_t)M * Ff);
+    __nv_bfloat16* hs = cw.take<__nv_bfloat16>((size_t)M * 3 * Ff);
+    AVEXK_CHECK_ARG(cw.ok, "avexk_beats_forward: workspace carve failed (fp32 mode)");
+    auto gemm3 = [&](const void* A, int K3, const __nv_bfloat16* W, int Nn, const float* bias, int gelu, float* raw, const float* res,
+                     float* o) -> int {
+      return gemm_bf16_launch(A, K3, W, K3, (int)M, Nn, K3, bias, gelu, raw, res, alpha, o, Nn, 0, st);
+    };
+    TRY(launch_posconv_fp32(x0, h->posconv_wf, h->posconv_b, tmp, B, N, G, C / G, d.conv_pos, st));
+    TRY(launch_layernorm(tmp, (int)M, C, h->enc_ln_w, h->enc_ln_b, d.ln_eps, x, xs, st, 1));
+    for (int li = 0; li < d.layers; ++li) {
+      const avexk_beats::Layer& L = h->layers[li];
+      const bool last = li == d.layers - 1;
+      TRY(gemm3(xs, 3 * C, L.qkv_w3, 3 * C, L.qkv_b, 0, nullptr, nullptr, qkv32));
+      TRY(launch_attention_fp32(qkv32, B, N, H, L.gate_w, L.gate_b, L.grep_a, bias_vec, key_pad, att32, st));
+      TRY(launch_split3_rows(att32, M, C, atts, st));
+      TRY(gemm3(atts, 3 * C, L.o_w3, C, L.o_b, 0, nullptr, x, tmp));
+      TRY(launch_layernorm(tmp, (int)M, C, L.ln1_w, L.ln1_b, d.ln_eps, x, xs, st, 1));
+      TRY(gemm3(xs, 3 * C, L.fc1_w3, Ff, L.fc1_b, 1, nullptr, nullptr, h32));
+      TRY(launch_split3_rows(h32, M, Ff, hs, st));
+      float* raw = hook_out ? hook_out[li + 1] : nullptr;
+      TRY(gemm3(hs, 3 * Ff, L.fc2_w3, C, L.fc2_b, 0, raw, x, tmp));
+      float* dst = (last && out) ? out : x;
+      TRY(launch_layernorm(tmp, (int)M, C, L.ln2_w, L.ln2_b, d.ln_eps, dst, last ? nullptr : xs, st, 1));
+      if (last && pooled) TRY(launch_mean_pool(dst, key_pad, key_pad != nullptr, B, N, C, pooled, st));
+    }
+    return AVEXK_OK;
+  }
   // ---- 12 post-LN DeepNorm blocks (backbone.py:350-373) --------------------------------------------------------------
   for (int li = 0; li < d.layers; ++li) {
     const avexk_beats::Layer& L = h->layers[li];

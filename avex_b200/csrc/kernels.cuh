@@ -27,6 +27,13 @@ int launch_mean_pool(const float* x, const uint8_t* key_pad, int any_pad, int B,
 int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
 int launch_posconv_pack(const float* v, const float* g, int C, int cg, int K, float* nrm_ws, __nv_bfloat16* W, cudaStream_t st);
 int launch_gate_pack(const float* w, const float* b, float* gw, float* gb, cudaStream_t st);
+// fp32_path.cu (fp32 mode)
+int launch_split3_rows(const float* src, long long M, int K, __nv_bfloat16* dst, cudaStream_t st);
+int launch_attention_fp32(const float* qkv, int B, int N, int H, const float* gate_w, const float* gate_b, const float* grep_a,
+                          const float* bias_vec, const uint8_t* key_pad, float* out, cudaStream_t st);
+int launch_posconv_pack_f32(const float* v, const float* g, const float* nrm, int G, int cg, int K, float* W, cudaStream_t st);
+int launch_posconv_fp32(const float* x0, const float* Wf, const float* bias, float* out, int B, int N, int G, int cg, int taps,
+                        cudaStream_t st);
 // posconv.cu
 int launch_posconv(const __nv_bfloat16* xg, const __nv_bfloat16* Wpc, const float* bias, const float* x0, float* out, int B,
                    int N, int G, int cg, int taps, cudaStream_t st);

@@ -198,6 +198,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = plugin.load_model("bench_beats_base", device="cuda", return_features_only=True).eval()
     bk = model.backbone
+    bk.precision = args.precision  # "bf16" (the metric) or "fp32" (validation mode; informational)
 
     B, T = args.batch, CLIP_SECONDS * SAMPLE_RATE
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -338,7 +339,8 @@ def run_ours(args):
 
     line = {
         "metric": "beats_embed_throughput", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": K_, "warmup": W_,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32 (3-term split-bf16 GEMMs, fp32 attention / pos-conv)",
         "data": "synthetic",
         "config": {"workload": "BEATs-base embedding extraction, 256 x 10 s clips @16 kHz per GPU, mean-pooled 768-d (BASELINE configs[1])",
                    "batch_per_gpu": B, "global_batch": world * B, "clip_seconds": CLIP_SECONDS, "tokens_per_clip": 496,
@@ -488,6 +490,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"], help="fp32: the <= 1e-3 validation mode (informational)")
     ap.add_argument("--workload", default="beats", choices=["beats", "effnet"],
                     help="beats (default): the BASELINE.json metric; effnet: secondary line for the EfficientNet-B0 path")
     args = ap.parse_args()

@@ -169,6 +169,12 @@ void avexk_beats_destroy(avexk_beats_t* h);
 /* Packs bf16 copies (fused QKV [3C,C], weight-norm resolved pos-conv, gate rows pre-summed). Synchronises. */
 int avexk_beats_load_weights(avexk_beats_t* h, const avexk_beats_weights* w, void* stream);
 
+/* fp32 mode (north_star: max-abs <= 1e-3 against the fp32 reference): every nn.Linear as a 3-term split-bf16 GEMM on the
+ * same tcgen05 kernel (K tripled, ~16 mantissa bits per operand), q/k/v/P, attention and the pos-conv in plain fp32 on the
+ * CUDA cores, fp32 residual stream as in the default mode.  Call BEFORE avexk_beats_load_weights (which packs the split
+ * weight copies); changes avexk_beats_workspace_bytes.  fp32_mode: 0 = bf16 operands (default), 1 = fp32 mode. */
+int avexk_beats_set_precision(avexk_beats_t* h, int fp32_mode);
+
 /* tokens for T samples: 8 * floor(num_frames(T) / 16). */
 int avexk_beats_num_tokens(int T);
 size_t avexk_beats_workspace_bytes(const avexk_beats_t* h, int B, int T);

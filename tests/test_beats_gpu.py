@@ -66,6 +66,30 @@ def test_against_reference_golden(cname):
     assert two.shape == (wav.shape[0], 2 * 768)
 
 
+@pytest.mark.parametrize("cname", list(cases.beats_cases()))
+def test_fp32_mode_against_reference_golden(cname):
+    """north_star fp32 mode: per-layer cosine >= 0.999 and max-abs <= 1e-3 against the reference run in fp32."""
+    case = cases.beats_cases()[cname]
+    g = np.load(os.path.join(G, f"beats_{cname}.npz"))
+    model, W = _build(case["layers"], case["wseed"], init=case.get("init", "perturbed"))
+    model.backbone.precision = "fp32"
+    wav = torch.from_numpy(case["wav"]).cuda()
+    mask = torch.from_numpy(case["mask"]).cuda() if "mask" in case else None
+    with torch.no_grad():
+        feats = model(wav, mask)
+    _cmp(f"fp32 {cname}/final", feats.cpu().numpy(), g["final"], atol=1e-3, cos_min=0.99999)
+    model.register_hooks_for_layers(["all"])
+    hooks = model.extract_embeddings(wav, padding_mask=mask, aggregation="none")
+    for li in case["keep_hooks"]:
+        _cmp(f"fp32 {cname}/hook{li}", hooks[li].cpu().numpy(), g[f"hook{li}"], atol=1e-3, cos_min=0.99999)
+    # switching back re-packs the bf16 engine
+    model.backbone.precision = "bf16"
+    model.deregister_all_hooks()
+    with torch.no_grad():
+        feats16 = model(wav, mask)
+    _cmp(f"bf16 again {cname}/final", feats16.cpu().numpy(), g["final"])
+
+
 def test_classifier_mode_masked_mean_pool():
     case = cases.beats_cases()["L2_2x2s_mask"]
     from avex_b200 import plugin
