@@ -7,8 +7,8 @@
 // permute/contiguous that follows.  Nothing of size N^2 touches HBM: the Toeplitz bias is the [H, 2N-1] vector
 // bias[h, j-i+N-1], indexed inside the score tile and scaled by the per-row gate.
 //
-// Persistent kernel, one CTA per SM, 18 warps.  A work item is (clip, head, pair of 128-query tiles); both tiles of the
-// pair share every K/V tile that streams through a 3-stage TMA ring, and their softmax phases interleave so the tensor
+// Persistent kernel, one CTA per SM, 20 warps (16 softmax, loader, MMA issuer, 2 register donors: setmaxnreg gives the
+// softmax warps 104 registers).  A work item is (clip, head, pair of 128-query tiles); both tiles of the pair share every K/V tile that streams through a 3-stage TMA ring, and their softmax phases interleave so the tensor
 // pipe, the MUFU pipe and the TMA engine are all busy:
 //   warps 0..7   softmax group A, warps 8..15 softmax group B.  thread = (query row r = 32*(warp&3)+lane, column half
 //                ch = (warp>>2)&1).  Per 128-key tile a thread reads its 64 scores from TMEM (tcgen05.ld), adds scale /
@@ -33,10 +33,13 @@ namespace {
 
 constexpr int BQ = 128, BKV = 128, HD = 64;
 constexpr int GROUP_WARPS = 8, GROUP_THREADS = 32 * GROUP_WARPS;
-constexpr int WARP_LOAD = 16, WARP_MMA = 17, NTHREADS = 32 * 18;
+constexpr int WARP_LOAD = 16, WARP_MMA = 17, NTHREADS = 32 * 20;  // warps 18-19: idle register donors (setmaxnreg is per warpgroup)
+// setmaxnreg moves registers inside the launch allocation: 640 x 96 = 61440 = 128*64 + 512*104
+constexpr int CTRL_REGS = 64, SOFTMAX_REGS = 104;
 constexpr int KV_STAGES = 3;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 domain: P stays below 2^8, exact after normalisation
+constexpr float P_CLAMP = 96.0f;           // a score more than 2^96 above the reference is clamped (row sums stay finite)
 
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 // Four copies of the 255-entry bias window per tile, copy s shifted right by s floats so that every row can read
@@ -49,7 +52,7 @@ constexpr int OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // [2 groups] x two 
 constexpr int OFF_TAB = OFF_P + 2 * 2 * TILE_BYTES;
 constexpr int TAB_WIN = 0;                               // [2][WIN_FLOATS] float
 constexpr int TAB_MASK = TAB_WIN + 2 * WIN_FLOATS * 4;  // [2][128] float
-constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] pass-A max / l, [2][128] gate
+constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] row sums l, [2][128] gate
 constexpr int TAB_BYTES = TAB_PMAX + 1024 * 4 + 16;  // + one int: first tile with a valid key
 constexpr int OFF_GATEW = OFF_TAB + 2 * TAB_BYTES;  // [2][64] float + [2] bias
 constexpr int OFF_BAR = OFF_GATEW + 640;
@@ -97,8 +100,7 @@ __device__ __forceinline__ void sts32(uint32_t addr, float v) {
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns (small chunks keep the softmax threads under the 96-register budget that 18
-// warps per SM allow)
+// 32 lanes x 16 consecutive fp32 columns (small chunks keep the softmax threads inside their 104 registers)
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -135,36 +137,35 @@ __device__ __forceinline__ int win_copy_offset(int s) { return s == 0 ? 0 : (s =
     hi = __fadd2_rn(hi, make_float2(mk.z, mk.w));                                                                         \
   }
 
-// Pass A (only on the first tile with a valid key): exact row max of this thread's 64 scores.
+// Reference estimate (only on the first tile with a valid key): the max of ONE 16-key chunk of the row, the chunk that holds
+// the clip's first valid key.  Both column halves of a row read the same chunk, so they agree without an exchange.  Any
+// reference within ~2^100 of the true row max is exact after the final 1/l (P is bf16: the precision is relative, the
+// reference only positions the exponent range); from the next tile on the reference follows the true running max.
 template <bool MASKED>
-__device__ __forceinline__ float score_max(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale) {
+__device__ __forceinline__ float score_est(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale) {
   float mx = -INFINITY;
-  const float2 g2 = make_float2(gate, gate), s2 = make_float2(qk_scale, qk_scale);
-  uint32_t ra[16], rb[16];
-  float4 w[4];
+  uint32_t ra[16];
   tmem_ld_32x16(taddr, ra);
+  float4 w[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = lds128(win_addr + k * 16);
   ptx::tmem_ld_wait();
 #pragma unroll
-  for (int chunk = 0; chunk < 4; ++chunk) {
-    if (chunk < 3) tmem_ld_32x16(taddr + (chunk + 1) * 16, (chunk & 1) ? ra : rb);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (chunk & 1) {
-        AVEXK_SCORE_QUAD(rb, lo, hi)
-        mx = fmaxf(fmaxf(mx, fmaxf(lo.x, lo.y)), fmaxf(hi.x, hi.y));
-      } else {
-        AVEXK_SCORE_QUAD(ra, lo, hi)
-        mx = fmaxf(fmaxf(mx, fmaxf(lo.x, lo.y)), fmaxf(hi.x, hi.y));
-      }
+  for (int k = 0; k < 4; ++k) {
+    float x0 = fmaf(__uint_as_float(ra[4 * k + 0]), qk_scale, gate * w[k].x);
+    float x1 = fmaf(__uint_as_float(ra[4 * k + 1]), qk_scale, gate * w[k].y);
+    float x2 = fmaf(__uint_as_float(ra[4 * k + 2]), qk_scale, gate * w[k].z);
+    float x3 = fmaf(__uint_as_float(ra[4 * k + 3]), qk_scale, gate * w[k].w);
+    if (MASKED) {
+      const float4 mk = lds128(mask_addr + k * 16);
+      x0 += mk.x; x1 += mk.y; x2 += mk.z; x3 += mk.w;
     }
-    if (chunk < 3) ptx::tmem_ld_wait();
+    mx = fmaxf(fmaxf(mx, fmaxf(x0, x1)), fmaxf(x2, x3));
   }
   return mx;
 }
 
-// Pass B: stream the 64 scores once: p = 2^(min(x - m, 126)) -> bf16 -> swizzled P row segment; accumulates the row
+// Stream the 64 scores once: p = 2^(min(x - m, P_CLAMP)) -> bf16 -> swizzled P row segment; accumulates the row
 // sum and tracks the tile max (used to move the reference max for the NEXT tile).  Nothing is kept in registers.
 template <bool MASKED>
 __device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale,
@@ -196,8 +197,8 @@ __device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, u
       lo_ = __fadd2_rn(lo_, nm2);
       hi_ = __fadd2_rn(hi_, nm2);
       // the reference max may lag the true max (it moves between tiles): clamp so bf16 P cannot overflow
-      const float2 p0 = make_float2(ex2(fminf(lo_.x, 126.f)), ex2(fminf(lo_.y, 126.f)));
-      const float2 p1 = make_float2(ex2(fminf(hi_.x, 126.f)), ex2(fminf(hi_.y, 126.f)));
+      const float2 p0 = make_float2(ex2(fminf(lo_.x, P_CLAMP)), ex2(fminf(lo_.y, P_CLAMP)));
+      const float2 p1 = make_float2(ex2(fminf(hi_.x, P_CLAMP)), ex2(fminf(hi_.y, P_CLAMP)));
       sum2 = __fadd2_rn(sum2, __fadd2_rn(p0, p1));
       pk[2 * k] = pack_bf16(p0.x, p0.y);
       pk[2 * k + 1] = pack_bf16(p1.x, p1.y);
@@ -232,7 +233,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
   const uint32_t smem_a = ptx::smem_u32(smem);
   unsigned char* sQ = smem + OFF_Q;
   unsigned char* sKV = smem + OFF_KV;
-  unsigned char* sP = smem + OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;     // [2]
   uint64_t* q_empty = bars + 2;    // [2]
@@ -281,6 +281,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == WARP_LOAD) {
+    ptx::setmaxnreg_dec<CTRL_REGS>();
     if (lane == 0) {
       // ===================== K/V loader =====================
       int stage = 0;
@@ -311,78 +312,89 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         }
       }
     }
+  } else if (warp > WARP_MMA) {
+    ptx::setmaxnreg_dec<CTRL_REGS>();  // register donors
   } else if (warp == WARP_MMA) {
+    ptx::setmaxnreg_dec<CTRL_REGS>();
     // ===================== MMA issuer =====================
     // Event loop over the two query tiles of the item: whichever group has delivered P_g(t) gets S_g(t+1) issued first
     // (it is on that group's critical path: its softmax warps are idle until it lands), then O_g += P_g(t) V(t).
+    // State is packed (done counters 16 bits per group, parities one bit per group) and barriers / descriptors are 32-bit
+    // shared addresses: the issuer thread lives in the 64 registers left after the softmax warps took theirs.
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD) | (1u << 16);  // B operand (V) is MN-major
-      uint32_t gt0 = 0;  // global index (over this CTA's items) of the item's first K/V tile
-      uint32_t items_g[2] = {0, 0}, tiles_g[2] = {0, 0};
+      const uint32_t bar_a = smem_a + OFF_BAR;
+      constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_KVFULL = 32, B_KVEMPTY = 64, B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
+      const uint32_t lo_q = ptx::sw128_desc_lo(smem_a + OFF_Q), lo_kv = ptx::sw128_desc_lo(smem_a + OFF_KV);
+      const uint32_t lo_p = ptx::sw128_desc_lo(smem_a + OFF_P);
+      uint32_t gt0 = 0;   // global index (over this CTA's items) of the item's first K/V tile
+      uint32_t ipar = 0;  // bit g: parity of the items group g has processed
+      uint32_t tpar = 0;  // bit g: parity of the tiles group g has processed
       auto issue_s = [&](int g, uint32_t gt) {
-        const int st = gt % KV_STAGES;
-        ptx::mbar_wait(&kv_full[st], (gt / KV_STAGES) & 1);  // returns at once if this phase was already observed
+        const uint32_t st = gt % KV_STAGES;
+        ptx::mbar_wait_a(bar_a + B_KVFULL + st * 8, (gt / KV_STAGES) & 1);  // returns at once if this phase was already observed
         ptx::tc_fence_after();
-        const uint64_t dq = ptx::make_sw128_desc(ptx::smem_u32(sQ + g * TILE_BYTES));
-        const uint64_t dk = ptx::make_sw128_desc(ptx::smem_u32(sKV + st * 2 * TILE_BYTES));
+        const uint32_t dq = lo_q + g * (TILE_BYTES >> 4), dk = lo_kv + st * (2 * TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          ptx::umma_bf16(tmem_base + g * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        ptx::umma_commit(&s_full[g]);
+          ptx::umma_bf16(tmem_base + g * 128, ptx::sw128_desc_from_lo(dq + 2 * k), ptx::sw128_desc_from_lo(dk + 2 * k), idesc_s,
+                         k != 0 ? 1u : 0u);
+        ptx::umma_commit_a(bar_a + B_SFULL + g * 8);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const Item it = decode_item(item, npairs, a.H, N);
-        const int ng = it.has_b ? 2 : 1;
+        const int ng = (item % npairs) * 2 * BQ + BQ < N ? 2 : 1;  // Item::has_b
         for (int g = 0; g < ng; ++g) {
-          ptx::mbar_wait(&q_full[g], items_g[g] & 1);
+          ptx::mbar_wait_a(bar_a + B_QFULL + g * 8, (ipar >> g) & 1);
           issue_s(g, gt0);
-          if (n_kv == 1) ptx::umma_commit(&q_empty[g]);
+          if (n_kv == 1) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);
         }
-        int done[2] = {0, ng == 2 ? 0 : n_kv};
-        while (done[0] < n_kv || done[1] < n_kv) {
-#pragma unroll
+        uint32_t done = ng == 2 ? 0u : (uint32_t)n_kv << 16;  // tiles finished: group 0 in the low half, group 1 in the high half
+        while ((int)(done & 0xffffu) < n_kv || (int)(done >> 16) < n_kv) {
+#pragma unroll 1
           for (int g = 0; g < 2; ++g) {
-            if (done[g] >= n_kv) continue;
-            if (!ptx::mbar_try_wait(&p_full[g], tiles_g[g] & 1)) continue;  // P_g(t) stored, S_g(t) read out of TMEM
-            const int t = done[g];
+            const int t = (done >> (16 * g)) & 0xffffu;
+            if (t >= n_kv) continue;
+            if (!ptx::mbar_try_wait_a(bar_a + B_PFULL + g * 8, (tpar >> g) & 1)) continue;  // P_g(t) stored, S_g(t) read out of TMEM
             if (t + 1 < n_kv) {
               // never block here: the stage of tile t+1 may only free up after the OTHER group's PV, issued by this thread
               const uint32_t gn = gt0 + t + 1;
-              if (!ptx::mbar_try_wait(&kv_full[gn % KV_STAGES], (gn / KV_STAGES) & 1)) continue;
+              if (!ptx::mbar_try_wait_a(bar_a + B_KVFULL + (gn % KV_STAGES) * 8, (gn / KV_STAGES) & 1)) continue;
             }
             ptx::tc_fence_after();
             if (t + 1 < n_kv) {
               issue_s(g, gt0 + t + 1);
-              if (t + 2 == n_kv) ptx::umma_commit(&q_empty[g]);  // last S of the item: Q_g may be overwritten
+              if (t + 2 == n_kv) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);  // last S of the item: Q_g may be overwritten
             }
             if (t == 0) {
-              ptx::mbar_wait(&o_free[g], (items_g[g] & 1) ^ 1);  // previous item's O_g has been drained
+              ptx::mbar_wait_a(bar_a + B_OFREE + g * 8, ((ipar >> g) & 1) ^ 1);  // previous item's O_g has been drained
               ptx::tc_fence_after();
             }
-            const int st = (gt0 + t) % KV_STAGES;
-            const uint64_t dp = ptx::make_sw128_desc(ptx::smem_u32(sP + g * 2 * TILE_BYTES));
-            const uint64_t dv = ptx::make_sw128_desc(ptx::smem_u32(sKV + st * 2 * TILE_BYTES + TILE_BYTES));
+            const uint32_t st = (gt0 + t) % KV_STAGES;
+            const uint32_t dp = lo_p + g * (2 * TILE_BYTES >> 4);
+            const uint32_t dv = lo_kv + st * (2 * TILE_BYTES >> 4) + (TILE_BYTES >> 4);
 #pragma unroll
             for (int ks = 0; ks < BKV / 16; ++ks) {
               // A: P, K-major, two 64-key swizzle atoms 16 KB apart; B: V rows = keys (MN-major), 16 keys = 2048 bytes
-              const uint64_t da = dp + (uint64_t)((ks >> 2) * (TILE_BYTES >> 4) + 2 * (ks & 3));
-              const uint64_t db = dv + (uint64_t)(ks * (2048 >> 4));
-              ptx::umma_bf16(tmem_base + 256 + g * 64, da, db, idesc_o, (t | ks) != 0 ? 1u : 0u);
+              const uint32_t da = dp + (ks >> 2) * (TILE_BYTES >> 4) + 2 * (ks & 3);
+              const uint32_t db = dv + ks * (2048 >> 4);
+              ptx::umma_bf16(tmem_base + 256 + g * 64, ptx::sw128_desc_from_lo(da), ptx::sw128_desc_from_lo(db), idesc_o,
+                             (t | ks) != 0 ? 1u : 0u);
             }
-            ptx::umma_commit(&o_full[g]);
-            ++done[g];
-            ++tiles_g[g];
+            ptx::umma_commit_a(bar_a + B_OFULL + g * 8);
+            done += 1u << (16 * g);
+            tpar ^= 1u << g;
             // the stage of tile t is free once both groups' MMAs on it retire; the group that issues last commits
-            if (ng == 1 || done[g ^ 1] > t) ptx::umma_commit(&kv_empty[st]);
+            if (ng == 1 || (int)((done >> (16 * (g ^ 1))) & 0xffffu) > t) ptx::umma_commit_a(bar_a + B_KVEMPTY + st * 8);
           }
         }
         gt0 += n_kv;
-        for (int g = 0; g < ng; ++g) ++items_g[g];
+        ipar ^= ng == 2 ? 3u : 1u;
       }
     }
   } else {
     // ===================== softmax groups =====================
+    ptx::setmaxnreg_inc<SOFTMAX_REGS>();
     const int g = warp >> 3;
     const int quarter = warp & 3, ch = (warp >> 2) & 1;
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
@@ -398,15 +410,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     const int shift = (r + 1) & 3;          // which shifted window copy makes (c - r + 127 + shift) a multiple of 4
     const uint32_t win_row = win_a + (win_copy_offset(shift) + ch * 64 - r + 127 + shift) * 4;
     const int bar_id = 1 + g;
-    const uint64_t* sfull = &s_full[g];
-    const uint64_t* ofull = &o_full[g];
-    uint32_t items = 0, tiles = 0;
+    // barrier addresses are derived from bar_a (32-bit shared address); par: bit 0 = item parity, bit 1 = tile parity
+    const uint32_t bar_a = smem_a + OFF_BAR + g * 8;
+    constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
+    uint32_t par = 0;
 
     // table entries of a tile: thread stid < 255 owns entry stid of the bias window, thread stid < 128 one mask entry
     auto fetch_bias = [&](const Item& it, int t) -> float {
       const int q0 = it.q0 + g * BQ;
       const int rel = t * BKV - q0 - 127 + stid;  // j - i
-      return (stid < 255 && rel > -N && rel < N) ? __ldg(a.bias_vec + (size_t)it.h * (2 * N - 1) + (N - 1) + rel) * LOG2E : 0.f;
+      return (stid < 255 && rel > -N && rel < N) ? __ldg(a.bias_vec + (it.h * (2 * N - 1) + (N - 1) + rel)) : 0.f;
     };
     auto fetch_dead = [&](const Item& it, int t) -> bool {
       const int j = t * BKV + stid;
@@ -417,6 +430,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     auto store_tables = [&](int t, float bv, bool dead) {
       const uint32_t wbuf = win_a + (t & 1) * WIN_FLOATS * 4;
       if (stid < 255) {
+        bv *= LOG2E;  // exp2 domain; scaled here so that the global load stays in flight across the tile
 #pragma unroll
         for (int s = 0; s < 4; ++s) sts32(wbuf + (win_copy_offset(s) + stid + s) * 4, bv);
       }
@@ -424,32 +438,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     };
     // tile-0 entries of the next item are fetched during the last tile of the current one (pref_*)
     bool have_pref = false;
-    float pref_bias = 0.f, pref_grep = 0.f;
+    float pref_bias = 0.f;
     bool pref_dead = false;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, npairs, a.H, N);
       if (g == 1 && !it.has_b) continue;
       const int q0 = it.q0 + g * BQ, b = it.b, h = it.h;
-      const uint8_t* kpad = has_pad ? a.key_pad + (size_t)b * N : nullptr;
       if (!have_pref) {
         pref_bias = fetch_bias(it, 0);
         pref_dead = fetch_dead(it, 0);
-        pref_grep = __ldg(a.grep_a + h);
       }
-      const float grep_a = pref_grep;
+      const float grep_a = __ldg(a.grep_a + h);  // 12 floats: an L1/L2 hit, consumed after the Q wait
       store_tables(0, pref_bias, pref_dead);
       have_pref = false;
-      Item nit = it;
-      bool next_ok = false;
-      if (item + (int)gridDim.x < n_items) {
-        nit = decode_item(item + gridDim.x, npairs, a.H, N);
-        next_ok = !(g == 1 && !nit.has_b);
-      }
 
       // first tile that holds a valid key (0 unless the clip starts with >= 128 padded keys): group-uniform
-      int t_first = 0;
+      int jc_first = 0;  // first valid key rounded down to its 16-key chunk: tile = jc_first / 128, chunk column = jc_first % 128
       if (has_pad) {
+        const uint8_t* kpad = a.key_pad + (size_t)b * N;
         int jmin = N;
         for (int j = stid; j < N; j += GROUP_THREADS)
           if (kpad[j] == 0) { jmin = j; break; }
@@ -457,11 +464,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         named_bar_sync(bar_id, GROUP_THREADS);
         if (jmin < N) atomicMin(reinterpret_cast<int*>(smem + OFF_TAB + g * TAB_BYTES + TAB_PMAX) + 1024, jmin);
         named_bar_sync(bar_id, GROUP_THREADS);
-        t_first = __float_as_int(lds32(pmax_a + 1024 * 4)) / BKV;  // == n_kv when every key is padded: pass A never runs
+        jc_first = __float_as_int(lds32(pmax_a + 1024 * 4)) & ~15;  // tile == n_kv when every key is padded: no estimate
       }
 
       // gate per query row from UNscaled q (backbone.py:544-550): thread ch computes sigmoid half ch, partners swap
-      ptx::mbar_wait(&q_full[g], items & 1);
+      ptx::mbar_wait_a(bar_a + B_QFULL, par & 1);
       float sg;
       {
         float acc0 = 0.f, acc1 = 0.f;
@@ -482,7 +489,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         sg = 1.0f / (1.0f + __expf(-z));
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&q_empty[g]);
+      if (lane == 0) ptx::mbar_arrive_a(bar_a + B_QEMPTY);
       sts32(pmax_a + (768 + ch * 128 + r) * 4, sg);
       named_bar_sync(bar_id, GROUP_THREADS);  // tables of tile 0 and the sigmoid halves are visible
       float gate;
@@ -492,7 +499,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         gate = ga * (gb * grep_a - 1.0f) + 2.0f;  // gate_a*(gate_b*grep_a-1)+2
       }
 
-      // m_run: reference max of the row (log2 domain).  Exact after pass A on tile t_first; afterwards it only moves
+      // m_run: reference max of the row (log2 domain).  An estimate on tile t_first (score_est); afterwards it only moves
       // (between tiles) when a tile's max exceeds it by more than RESCALE_THRESHOLD -- O and l are rescaled by
       // `pending` at the start of the next tile.  The result is exact after the final 1/l for any reference.
       float m_run = -INFINITY, l_run = 0.f, pending = 1.0f;
@@ -504,26 +511,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         if (more) {  // global loads in flight during the tile
           nbias = fetch_bias(it, t + 1);
           ndead = fetch_dead(it, t + 1);
-        } else if (next_ok) {
-          pref_bias = fetch_bias(nit, 0);
-          pref_dead = fetch_dead(nit, 0);
-          pref_grep = __ldg(a.grep_a + nit.h);
-          have_pref = true;
+        } else if (item + (int)gridDim.x < n_items) {  // decoded here, not held in registers across the tiles
+          const Item nit = decode_item(item + gridDim.x, npairs, a.H, N);
+          if (!(g == 1 && !nit.has_b)) {
+            pref_bias = fetch_bias(nit, 0);
+            pref_dead = fetch_dead(nit, 0);
+            have_pref = true;
+          }
         }
         const uint32_t taddr = tmem_s + lane_addr + ch * 64;
         const uint32_t wrow = win_row + (t & 1) * WIN_FLOATS * 4;
         const uint32_t mrow = mask_a + ((t & 1) * BKV + ch * 64) * 4;
-        ptx::mbar_wait(const_cast<uint64_t*>(sfull), tiles & 1);
+        ptx::mbar_wait_a(bar_a + B_SFULL, (par >> 1) & 1);
         ptx::tc_fence_after();
-        if (t == t_first) {
-          const float pm = masked ? score_max<true>(taddr, wrow, mrow, gate, qk_scale)
-                                  : score_max<false>(taddr, wrow, mrow, gate, qk_scale);
-          sts32(pmax_a + (512 + ch * 128 + r) * 4, pm);
-          named_bar_sync(bar_id, GROUP_THREADS);
-          m_run = fmaxf(pm, lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4));  // finite: the tile has a valid key
+        if (t == jc_first / BKV) {  // finite: the chunk holds a valid key
+          const int c_first = jc_first % BKV;
+          const uint32_t ta = tmem_s + lane_addr + c_first, wa = wrow + (c_first - ch * 64) * 4;
+          const uint32_t ma = mask_a + ((t & 1) * BKV + c_first) * 4;
+          m_run = masked ? score_est<true>(ta, wa, ma, gate, qk_scale) : score_est<false>(ta, wa, ma, gate, qk_scale);
         }
         if (t > 0) {
-          ptx::mbar_wait(const_cast<uint64_t*>(ofull), (tiles - 1) & 1);  // PV(t-1) retired: O consistent, P buffer free
+          ptx::mbar_wait_a(bar_a + B_OFULL, ((par >> 1) & 1) ^ 1);  // PV(t-1) retired: O consistent, P buffer free
           ptx::tc_fence_after();
           if (__any_sync(0xffffffffu, pending != 1.0f)) {
             l_run *= pending;
@@ -548,8 +556,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         ptx::fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async proxy
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[g]);
-        ++tiles;
+        if (lane == 0) ptx::mbar_arrive_a(bar_a + B_PFULL);
+        par ^= 2;
         // off the critical path: join the tile max with the partner, decide the reference for the next tile
         pending = 1.0f;
         if (more) {
@@ -565,19 +573,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
       }
 
       // ---- finalise: O / l -> bf16 -------------------------------------------------------------------------------
-      named_bar_sync(bar_id, GROUP_THREADS);  // pass-A exchange slots are free again
       sts32(pmax_a + (512 + ch * 128 + r) * 4, l_run);
       named_bar_sync(bar_id, GROUP_THREADS);
       const float l_tot = l_run + lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4);
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-      ptx::mbar_wait(const_cast<uint64_t*>(ofull), (tiles - 1) & 1);
+      ptx::mbar_wait_a(bar_a + B_OFULL, ((par >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       uint32_t o[32];
       ptx::tmem_ld_32x32(tmem_o + lane_addr + ch * 32, o);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&o_free[g]);  // O_g is in registers: the next item's first PV may overwrite it
+      if (lane == 0) ptx::mbar_arrive_a(bar_a + B_OFREE);  // O_g is in registers: the next item's first PV may overwrite it
       if (q0 + r < N) {
         __nv_bfloat16* dst = a.out + ((size_t)b * N + q0 + r) * (size_t)(a.H * HD) + h * HD + ch * 32;
 #pragma unroll
@@ -590,7 +597,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
           *reinterpret_cast<uint4*>(dst + c * 8) = pk;
         }
       }
-      ++items;
+      par ^= 1;
     }
   }
 
@@ -610,7 +617,8 @@ extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const
                                      void* stream) {
   using namespace avexk;
   AVEXK_CHECK_ARG(qkv && gate_w && gate_b && grep_a && bias_vec && out, "avexk_attention_gated: null argument");
-  AVEXK_CHECK_ARG(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535, "avexk_attention_gated: bad shape B=%d N=%d H=%d", B, N, H);
+  AVEXK_CHECK_ARG(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535 && (long long)H * (2LL * N - 1) < (1LL << 31),
+                  "avexk_attention_gated: bad shape B=%d N=%d H=%d", B, N, H);
   AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   "avexk_attention_gated: qkv/out must be 16-byte aligned");
   if (B == 0) return AVEXK_OK;

@@ -182,7 +182,7 @@ def test_attention_gated(lib, B, N, H, pad):
 
 
 def test_attention_leading_padding(lib):
-    """Keys 0..139 of clip 0 are padded: the first 128-key tile is fully masked (exercises the deferred exact-max pass)."""
+    """Keys 0..139 of clip 0 are padded: the first 128-key tile is fully masked (the reference estimate is taken from the chunk of the first valid key)."""
     B, N, H = 2, 300, 3
     g = torch.Generator(device="cuda").manual_seed(5)
     qkv = (torch.randn(B * N, 3 * H * 64, device="cuda", generator=g) * 2.0).to(torch.bfloat16)
@@ -225,6 +225,34 @@ def test_attention_large_score_growth(lib):
     err = (out.float() - ref).abs().max().item()
     assert err <= 3e-2, err
     assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
+
+
+def test_attention_reference_lags_row_max(lib):
+    """The softmax reference of a row is estimated from its first 16 valid keys; here every later key scores far higher
+    (row max ~ 2^50 above the estimate), so P is formed against a lagging reference and rescaled after the first tile."""
+    B, N, H = 2, 496, 2
+    g = torch.Generator(device="cuda").manual_seed(21)
+    qkv = torch.randn(B * N, 3 * H * 64, device="cuda", generator=g)
+    k = qkv[:, H * 64 : 2 * H * 64].view(B, N, H * 64)
+    k[:, 16:] *= 12.0
+    qkv = qkv.to(torch.bfloat16)
+    gw = torch.randn(2, 64, device="cuda", generator=g) * 0.2
+    gb = torch.randn(2, device="cuda", generator=g) * 0.2
+    ga = 1.0 + 0.2 * torch.randn(H, device="cuda", generator=g)
+    table = torch.randn(320, H, generator=torch.Generator().manual_seed(4))
+    bias_vec = torch.from_numpy(OR.bias_vector(table.numpy(), N)).cuda()
+    for key_pad in (None, torch.zeros(B, N, dtype=torch.uint8, device="cuda")):
+        if key_pad is not None:
+            key_pad[0, :5] = 1  # the estimate chunk starts with masked keys
+            key_pad[1, 400:] = 1
+        out = torch.empty(B * N, H * 64, device="cuda", dtype=torch.bfloat16)
+        _check(lib.avexk_attention_gated(qkv.data_ptr(), B, N, H, gw.data_ptr(), gb.data_ptr(), ga.data_ptr(), bias_vec.data_ptr(),
+                                         key_pad.data_ptr() if key_pad is not None else None, out.data_ptr(), _stream()), lib)  # fmt: skip
+        ref = _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, key_pad)
+        assert torch.isfinite(out.float()).all()
+        err = (out.float() - ref).abs().max().item()
+        assert err <= 3e-2, err
+        assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
 
 
 @pytest.mark.parametrize("B,N,pad", [(2, 48, False), (1, 248, False), (2, 131, True), (3, 496, False)])
