@@ -20,7 +20,7 @@
 //                zero-filled by hardware), running ahead across work items; lane 1 loads the Q tiles.
 //   warp 17      MMA issuer: S_g = Q_g K^T (128x128x64, K-major operands) and O_g += P_g V (128x64x128, V consumed
 //                MN-major exactly as it lies in the qkv buffer -- no transposed copy), tcgen05.commit -> mbarriers.
-//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each), O_A @256, O_B @320 (fp32 128x64 each).
+//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each), O_A @256, O_B @320 (fp32 128x64 each), gate logits @384 / @400.
 // Roofline: MUFU (one ex2 per score: B*H*N^2 per layer) and FP32 issue, not the tensor pipe; see DESIGN.md section 4.
 #include <math.h>
 
@@ -49,13 +49,14 @@ constexpr int WIN_FLOATS = 1056;
 constexpr int OFF_Q = 0;                                 // [2] tiles
 constexpr int OFF_KV = OFF_Q + 2 * TILE_BYTES;           // [KV_STAGES] x (K tile, V tile)
 constexpr int OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // [2 groups] x two 64-key atoms
-constexpr int OFF_TAB = OFF_P + 2 * 2 * TILE_BYTES;
+constexpr int OFF_WG = OFF_P + 2 * 2 * TILE_BYTES;  // gate weights as a 16 x 64 bf16 UMMA operand (K-major, 128-byte swizzle)
+constexpr int OFF_TAB = OFF_WG + 2048;
 constexpr int TAB_WIN = 0;                               // [2][WIN_FLOATS] float
 constexpr int TAB_MASK = TAB_WIN + 2 * WIN_FLOATS * 4;  // [2][128] float
-constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] row sums l, [2][128] gate
+constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] row sums l
 constexpr int TAB_BYTES = TAB_PMAX + 1024 * 4 + 16;  // + one int: first tile with a valid key
-constexpr int OFF_GATEW = OFF_TAB + 2 * TAB_BYTES;  // [2][64] float + [2] bias
-constexpr int OFF_BAR = OFF_GATEW + 640;
+constexpr int OFF_GATEB = OFF_TAB + 2 * TAB_BYTES;  // [2] float: gate bias
+constexpr int OFF_BAR = OFF_GATEB + 16;
 constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "attention_tc: shared memory budget");
 
@@ -82,11 +83,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ float lds32(uint32_t addr) {
@@ -250,16 +246,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
   const int npairs = (N + 2 * BQ - 1) / (2 * BQ);
   const int n_items = a.B * a.H * npairs;
 
-  if (tid < 130) {  // gate weights [2][64] + bias [2] -> shared memory, once per CTA
-    const float v = tid < 128 ? __ldg(a.gate_w + tid) : __ldg(a.gate_b + tid - 128);
-    sts32(smem_a + OFF_GATEW + tid * 4, v);
+  // Gate weights -> a 16-row UMMA B operand, once per CTA: rows 0,1 = bf16(w), rows 2,3 = bf16(w - hi) (the two halves
+  // are summed after the MMA, so the gate logits carry ~16 mantissa bits of w), rows 4..15 = 0.
+  for (int e = tid; e < 16 * HD; e += NTHREADS) {
+    const int row = e >> 6, col = e & 63;
+    const float w = row < 4 ? __ldg(a.gate_w + (row & 1) * HD + col) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 v = row < 2 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
+    const uint32_t off = row * 128 + (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2;
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_a + OFF_WG + off), "h"(__bfloat16_as_ushort(v)) : "memory");
   }
+  if (tid < 2) sts32(smem_a + OFF_GATEB + tid * 4, __ldg(a.gate_b + tid));
+  ptx::fence_proxy_async();  // the gate operand is read by the tensor core (async proxy)
   if (warp == WARP_MMA) {
     if (lane == 0) {
       ptx::prefetch_tensormap(&map_qkv);
       for (int g = 0; g < 2; ++g) {
         ptx::mbar_init(&q_full[g], 1);
-        ptx::mbar_init(&q_empty[g], GROUP_WARPS + 1);  // gate readers + the commit of the item's last S MMA
+        ptx::mbar_init(&q_empty[g], 1);  // the commit of the item's last S MMA
         ptx::mbar_init(&s_full[g], 1);
         ptx::mbar_init(&p_full[g], GROUP_WARPS);
         ptx::mbar_init(&o_full[g], 1);
@@ -324,6 +328,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD) | (1u << 16);  // B operand (V) is MN-major
+      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(BQ, 16);
+      const uint32_t lo_wg = ptx::sw128_desc_lo(smem_a + OFF_WG);
       const uint32_t bar_a = smem_a + OFF_BAR;
       constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_KVFULL = 32, B_KVEMPTY = 64, B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
       const uint32_t lo_q = ptx::sw128_desc_lo(smem_a + OFF_Q), lo_kv = ptx::sw128_desc_lo(smem_a + OFF_KV);
@@ -346,6 +352,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         const int ng = (item % npairs) * 2 * BQ + BQ < N ? 2 : 1;  // Item::has_b
         for (int g = 0; g < ng; ++g) {
           ptx::mbar_wait_a(bar_a + B_QFULL + g * 8, (ipar >> g) & 1);
+          ptx::tc_fence_after();
+          // gate logits of the 128 query rows: G_g = Q_g Wg^T (128 x 16 x 64) -> TMEM columns 384 + 16 g; the commit of
+          // S_g(0) below covers them
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::umma_bf16(tmem_base + 384 + g * 16, ptx::sw128_desc_from_lo(lo_q + g * (TILE_BYTES >> 4) + 2 * k),
+                           ptx::sw128_desc_from_lo(lo_wg + 2 * k), idesc_g, k != 0 ? 1u : 0u);
           issue_s(g, gt0);
           if (n_kv == 1) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);
         }
@@ -403,7 +416,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     const uint32_t tmem_s = tmem_base + g * 128, tmem_o = tmem_base + 256 + g * 64;
     const uint32_t tab_a = smem_a + OFF_TAB + g * TAB_BYTES;
     const uint32_t win_a = tab_a + TAB_WIN, mask_a = tab_a + TAB_MASK, pmax_a = tab_a + TAB_PMAX;
-    const uint32_t q_a = smem_a + OFF_Q + g * TILE_BYTES + r * 128;
     const uint32_t p_a = smem_a + OFF_P + g * 2 * TILE_BYTES + ch * TILE_BYTES + r * 128;
     const bool has_pad = a.key_pad != nullptr;
     const float qk_scale = 0.125f * LOG2E;  // head_dim^-0.5 (backbone.py:403), exp2 domain
@@ -412,7 +424,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     const int bar_id = 1 + g;
     // barrier addresses are derived from bar_a (32-bit shared address); par: bit 0 = item parity, bit 1 = tile parity
     const uint32_t bar_a = smem_a + OFF_BAR + g * 8;
-    constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
+    constexpr uint32_t B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
     uint32_t par = 0;
 
     // table entries of a tile: thread stid < 255 owns entry stid of the bias window, thread stid < 128 one mask entry
@@ -427,31 +439,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
       if (stid < BKV && !dead && has_pad) dead = a.key_pad[(size_t)it.b * N + j] != 0;
       return dead;
     };
-    auto store_tables = [&](int t, float bv, bool dead) {
-      const uint32_t wbuf = win_a + (t & 1) * WIN_FLOATS * 4;
+    auto store_tables = [&](uint32_t slot, float bv, bool dead) {
+      const uint32_t wbuf = win_a + slot * WIN_FLOATS * 4;
       if (stid < 255) {
         bv *= LOG2E;  // exp2 domain; scaled here so that the global load stays in flight across the tile
 #pragma unroll
         for (int s = 0; s < 4; ++s) sts32(wbuf + (win_copy_offset(s) + stid + s) * 4, bv);
       }
-      if (stid < BKV) sts32(mask_a + ((t & 1) * BKV + stid) * 4, dead ? -INFINITY : 0.f);
+      if (stid < BKV) sts32(mask_a + (slot * BKV + stid) * 4, dead ? -INFINITY : 0.f);
     };
-    // tile-0 entries of the next item are fetched during the last tile of the current one (pref_*)
-    bool have_pref = false;
-    float pref_bias = 0.f;
-    bool pref_dead = false;
+    // The table slot of a tile is the parity of the group's running tile count (par bit 1), so slots alternate across item
+    // boundaries too: the tables of the NEXT item's first tile are fetched and stored during the last tile of the current
+    // one (have_tab) and published by the barrier of the finalisation.
+    bool have_tab = false;
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, npairs, a.H, N);
       if (g == 1 && !it.has_b) continue;
       const int q0 = it.q0 + g * BQ, b = it.b, h = it.h;
-      if (!have_pref) {
-        pref_bias = fetch_bias(it, 0);
-        pref_dead = fetch_dead(it, 0);
-      }
-      const float grep_a = __ldg(a.grep_a + h);  // 12 floats: an L1/L2 hit, consumed after the Q wait
-      store_tables(0, pref_bias, pref_dead);
-      have_pref = false;
+      if (!have_tab) store_tables((par >> 1) & 1, fetch_bias(it, 0), fetch_dead(it, 0));
+      const float grep_a = __ldg(a.grep_a + h);  // 12 floats: an L1/L2 hit, consumed after the first S wait
 
       // first tile that holds a valid key (0 unless the clip starts with >= 128 padded keys): group-uniform
       int jc_first = 0;  // first valid key rounded down to its 16-key chunk: tile = jc_first / 128, chunk column = jc_first % 128
@@ -467,37 +474,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         jc_first = __float_as_int(lds32(pmax_a + 1024 * 4)) & ~15;  // tile == n_kv when every key is padded: no estimate
       }
 
-      // gate per query row from UNscaled q (backbone.py:544-550): thread ch computes sigmoid half ch, partners swap
-      ptx::mbar_wait_a(bar_a + B_QFULL, par & 1);
-      float sg;
-      {
-        float acc0 = 0.f, acc1 = 0.f;
-        const uint32_t gw_a = smem_a + OFF_GATEW + ch * 256;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 raw = lds128u(q_a + ((c ^ (r & 7)) << 4));
-          const float4 w0 = lds128(gw_a + c * 32), w1 = lds128(gw_a + c * 32 + 16);
-          const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-          const float2 f0 = __bfloat1622float2(p2[0]), f1 = __bfloat1622float2(p2[1]);
-          const float2 f2 = __bfloat1622float2(p2[2]), f3 = __bfloat1622float2(p2[3]);
-          acc0 = fmaf(f0.x, w0.x, acc0); acc1 = fmaf(f0.y, w0.y, acc1);
-          acc0 = fmaf(f1.x, w0.z, acc0); acc1 = fmaf(f1.y, w0.w, acc1);
-          acc0 = fmaf(f2.x, w1.x, acc0); acc1 = fmaf(f2.y, w1.y, acc1);
-          acc0 = fmaf(f3.x, w1.z, acc0); acc1 = fmaf(f3.y, w1.w, acc1);
-        }
-        const float z = acc0 + acc1 + lds32(smem_a + OFF_GATEW + 512 + ch * 4);
-        sg = 1.0f / (1.0f + __expf(-z));
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_a(bar_a + B_QEMPTY);
-      sts32(pmax_a + (768 + ch * 128 + r) * 4, sg);
-      named_bar_sync(bar_id, GROUP_THREADS);  // tables of tile 0 and the sigmoid halves are visible
-      float gate;
-      {
-        const float other = lds32(pmax_a + (768 + (ch ^ 1) * 128 + r) * 4);
-        const float ga = ch == 0 ? sg : other, gb = ch == 0 ? other : sg;
-        gate = ga * (gb * grep_a - 1.0f) + 2.0f;  // gate_a*(gate_b*grep_a-1)+2
-      }
+      if (!have_tab && !has_pad) named_bar_sync(bar_id, GROUP_THREADS);  // tables of the first tile are visible
+      have_tab = false;
+      float gate = 0.f;  // set on the item's first tile
 
       // m_run: reference max of the row (log2 domain).  An estimate on tile t_first (score_est); afterwards it only moves
       // (between tiles) when a tile's max exceeds it by more than RESCALE_THRESHOLD -- O and l are rescaled by
@@ -514,24 +493,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         } else if (item + (int)gridDim.x < n_items) {  // decoded here, not held in registers across the tiles
           const Item nit = decode_item(item + gridDim.x, npairs, a.H, N);
           if (!(g == 1 && !nit.has_b)) {
-            pref_bias = fetch_bias(nit, 0);
-            pref_dead = fetch_dead(nit, 0);
-            have_pref = true;
+            nbias = fetch_bias(nit, 0);
+            ndead = fetch_dead(nit, 0);
+            have_tab = true;
           }
         }
+        const uint32_t slot = (par >> 1) & 1;
         const uint32_t taddr = tmem_s + lane_addr + ch * 64;
-        const uint32_t wrow = win_row + (t & 1) * WIN_FLOATS * 4;
-        const uint32_t mrow = mask_a + ((t & 1) * BKV + ch * 64) * 4;
-        ptx::mbar_wait_a(bar_a + B_SFULL, (par >> 1) & 1);
+        const uint32_t wrow = win_row + slot * WIN_FLOATS * 4;
+        const uint32_t mrow = mask_a + (slot * BKV + ch * 64) * 4;
+        ptx::mbar_wait_a(bar_a + B_SFULL, slot);
         ptx::tc_fence_after();
+        if (t == 0) {
+          // gate of this query row from UNscaled q (backbone.py:544-550): the logits q.w_a, q.w_b were formed by the
+          // tensor core next to S_g(0) (hi and lo halves of w in columns 0,1 and 2,3); both column halves of the row
+          // read the same values: gate = sig_a * (sig_b * grep_a - 1) + 2
+          uint32_t z[4];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(z[0]), "=r"(z[1]), "=r"(z[2]), "=r"(z[3])
+                       : "r"(tmem_base + 384 + g * 16 + lane_addr)
+                       : "memory");
+          ptx::tmem_ld_wait();
+          const float za = __uint_as_float(z[0]) + __uint_as_float(z[2]) + lds32(smem_a + OFF_GATEB);
+          const float zb = __uint_as_float(z[1]) + __uint_as_float(z[3]) + lds32(smem_a + OFF_GATEB + 4);
+          const float ga = 1.0f / (1.0f + __expf(-za)), gb = 1.0f / (1.0f + __expf(-zb));
+          gate = ga * (gb * grep_a - 1.0f) + 2.0f;
+        }
         if (t == jc_first / BKV) {  // finite: the chunk holds a valid key
           const int c_first = jc_first % BKV;
           const uint32_t ta = tmem_s + lane_addr + c_first, wa = wrow + (c_first - ch * 64) * 4;
-          const uint32_t ma = mask_a + ((t & 1) * BKV + c_first) * 4;
+          const uint32_t ma = mask_a + (slot * BKV + c_first) * 4;
           m_run = masked ? score_est<true>(ta, wa, ma, gate, qk_scale) : score_est<false>(ta, wa, ma, gate, qk_scale);
         }
         if (t > 0) {
-          ptx::mbar_wait_a(bar_a + B_OFULL, ((par >> 1) & 1) ^ 1);  // PV(t-1) retired: O consistent, P buffer free
+          ptx::mbar_wait_a(bar_a + B_OFULL, slot ^ 1);  // PV(t-1) retired: O consistent, P buffer free
           ptx::tc_fence_after();
           if (__any_sync(0xffffffffu, pending != 1.0f)) {
             l_run *= pending;
@@ -561,14 +556,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         // off the critical path: join the tile max with the partner, decide the reference for the next tile
         pending = 1.0f;
         if (more) {
-          sts32(pmax_a + (((t & 1) * 2 + ch) * 128 + r) * 4, mx);
-          store_tables(t + 1, nbias, ndead);
+          sts32(pmax_a + ((slot * 2 + ch) * 128 + r) * 4, mx);
+          store_tables(slot ^ 1, nbias, ndead);
           named_bar_sync(bar_id, GROUP_THREADS);
-          const float m_tile = fmaxf(mx, lds32(pmax_a + (((t & 1) * 2 + (ch ^ 1)) * 128 + r) * 4));
+          const float m_tile = fmaxf(mx, lds32(pmax_a + ((slot * 2 + (ch ^ 1)) * 128 + r) * 4));
           if (m_run != -INFINITY && m_tile > m_run + RESCALE_THRESHOLD) {
             pending = ex2(m_run - m_tile);
             m_run = m_tile;
           }
+        } else if (have_tab) {
+          store_tables(slot ^ 1, nbias, ndead);  // first tile of the next item; published by the barrier below
         }
       }
 
