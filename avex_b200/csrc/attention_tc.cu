@@ -13,14 +13,18 @@
 //   warps 0..7   softmax group A, warps 8..15 softmax group B.  thread = (query row r = 32*(warp&3)+lane, column half
 //                ch = (warp>>2)&1).  Per 128-key tile a thread reads its 64 scores from TMEM (tcgen05.ld), adds scale /
 //                gated bias / mask, joins the row max with its partner through shared memory, exponentiates
-//                (ex2.approx) and writes the bf16 P row segment straight into the 128-byte-swizzled K-major layout the
-//                UMMA descriptor expects.  The running max is lazy (FA4-style): O in TMEM is only rescaled when the
+//                (ex2.approx) and writes P as bf16 pairs back into TMEM over its own score columns, where the PV MMA reads
+//                it as its A operand (P never touches shared memory).  The running max is lazy (FA4-style): O in TMEM is only rescaled when the
 //                max grows by more than 2^8, which is exact after the final 1/l.
 //   warp 16      loaders: lane 0 streams 128-key K and V tiles (3-D tensor map: rows past the clip end are
 //                zero-filled by hardware), running ahead across work items; lane 1 loads the Q tiles.
-//   warp 17      MMA issuer: S_g = Q_g K^T (128x128x64, K-major operands) and O_g += P_g V (128x64x128, V consumed
-//                MN-major exactly as it lies in the qkv buffer -- no transposed copy), tcgen05.commit -> mbarriers.
-//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each), O_A @256, O_B @320 (fp32 128x64 each), gate logits @384 / @400.
+//   warp 17      MMA issuer: S_g = Q_g K^T (128x128x64, K-major operands from shared memory), the gate logits Q_g Wg^T, and
+//                O_g += P_g V (128x64x128; A = P from TMEM, B = V consumed MN-major exactly as it lies in the qkv buffer --
+//                no transposed copy), tcgen05.commit -> mbarriers.  PV_g(t) is issued before S_g(t+1), which overwrites P.
+//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each; P_g as bf16 pairs over columns 0..31 and 64..95 of S_g),
+//                O_A @256, O_B @320 (fp32 128x64 each), gate logits @384 / @400.
+//   Shared memory: Q (2 tiles), a 5-stage K/V ring, the bias / mask tables -- the measured limiter before P moved to TMEM
+//                was the shared-memory pipe (64 % busy: bias-window loads 31 %, P stores 11 %, MMA operand reads 21 %).
 // Roofline: MUFU (one ex2 per score: B*H*N^2 per layer) and FP32 issue, not the tensor pipe; see DESIGN.md section 4.
 #include <math.h>
 
@@ -36,7 +40,7 @@ constexpr int GROUP_WARPS = 8, GROUP_THREADS = 32 * GROUP_WARPS;
 constexpr int WARP_LOAD = 16, WARP_MMA = 17, NTHREADS = 32 * 20;  // warps 18-19: idle register donors (setmaxnreg is per warpgroup)
 // setmaxnreg moves registers inside the launch allocation: 640 x 96 = 61440 = 128*64 + 512*104
 constexpr int CTRL_REGS = 64, SOFTMAX_REGS = 104;
-constexpr int KV_STAGES = 3;
+constexpr int KV_STAGES = 5;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 domain: P stays below 2^8, exact after normalisation
 constexpr float P_CLAMP = 96.0f;           // a score more than 2^96 above the reference is clamped (row sums stay finite)
@@ -48,12 +52,11 @@ constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 constexpr int WIN_FLOATS = 1056;
 constexpr int OFF_Q = 0;                                 // [2] tiles
 constexpr int OFF_KV = OFF_Q + 2 * TILE_BYTES;           // [KV_STAGES] x (K tile, V tile)
-constexpr int OFF_P = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // [2 groups] x two 64-key atoms
-constexpr int OFF_WG = OFF_P + 2 * 2 * TILE_BYTES;  // gate weights as a 16 x 64 bf16 UMMA operand (K-major, 128-byte swizzle)
+constexpr int OFF_WG = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // gate weights as a 16 x 64 bf16 UMMA operand (K-major, 128-byte swizzle)
 constexpr int OFF_TAB = OFF_WG + 2048;
 constexpr int TAB_WIN = 0;                               // [2][WIN_FLOATS] float
 constexpr int TAB_MASK = TAB_WIN + 2 * WIN_FLOATS * 4;  // [2][128] float
-constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] row sums l
+constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] row sums l, [128] shared estimate
 constexpr int TAB_BYTES = TAB_PMAX + 1024 * 4 + 16;  // + one int: first tile with a valid key
 constexpr int OFF_GATEB = OFF_TAB + 2 * TAB_BYTES;  // [2] float: gate bias
 constexpr int OFF_BAR = OFF_GATEB + 16;
@@ -92,9 +95,6 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns (small chunks keep the softmax threads inside their 104 registers)
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -161,11 +161,13 @@ __device__ __forceinline__ float score_est(uint32_t taddr, uint32_t win_addr, ui
   return mx;
 }
 
-// Stream the 64 scores once: p = 2^(min(x - m, P_CLAMP)) -> bf16 -> swizzled P row segment; accumulates the row
-// sum and tracks the tile max (used to move the reference max for the NEXT tile).  Nothing is kept in registers.
+// Stream the 64 scores once: p = 2^(min(x - m, P_CLAMP)) -> bf16 pairs -> back into TMEM, over the first half of the
+// thread's own score columns (chunk c of 16 fp32 scores becomes 8 packed columns at 8c: always columns this thread has
+// already read), where the PV MMA takes them as its A operand -- P never touches shared memory.  Accumulates the row sum
+// and tracks the tile max (used to move the reference max for the NEXT tile).  Nothing is kept in registers.
 template <bool MASKED>
 __device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale,
-                                            float m_ref, uint32_t p_row, int rsw, float& mx_out, float& sum_out) {
+                                            float m_ref, float& mx_out, float& sum_out) {
   float mx = -INFINITY;
   const float2 g2 = make_float2(gate, gate), s2 = make_float2(qk_scale, qk_scale), nm2 = make_float2(-m_ref, -m_ref);
   float2 sum2 = make_float2(0.f, 0.f);
@@ -199,10 +201,12 @@ __device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, u
       pk[2 * k] = pack_bf16(p0.x, p0.y);
       pk[2 * k + 1] = pack_bf16(p1.x, p1.y);
     }
-    sts128u(p_row + (((chunk * 2) ^ rsw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-    sts128u(p_row + (((chunk * 2 + 1) ^ rsw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
-    if (chunk < 3) ptx::tmem_ld_wait();
+    if (chunk < 3) ptx::tmem_ld_wait();  // also orders the store below after the loads of the columns it overwrites
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + chunk * 8),
+                 "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                 : "memory");
   }
+  tmem_st_wait();
   mx_out = mx;
   sum_out = sum2.x + sum2.y;
 }
@@ -232,13 +236,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;     // [2]
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* kv_full = bars + 4;    // [KV_STAGES]
-  uint64_t* kv_empty = bars + 8;   // [KV_STAGES]
-  uint64_t* s_full = bars + 12;    // [2]
-  uint64_t* p_full = bars + 14;    // [2]
-  uint64_t* o_full = bars + 16;    // [2]
-  uint64_t* o_free = bars + 18;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* kv_full = bars + 4;    // [KV_STAGES <= 8]
+  uint64_t* kv_empty = bars + 12;  // [KV_STAGES <= 8]
+  uint64_t* s_full = bars + 20;    // [2]
+  uint64_t* p_full = bars + 22;    // [2]
+  uint64_t* o_full = bars + 24;    // [2]
+  uint64_t* o_free = bars + 26;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  static_assert(KV_STAGES <= 8, "barrier layout");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N;
@@ -331,9 +336,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
       constexpr uint32_t idesc_g = ptx::make_idesc_bf16(BQ, 16);
       const uint32_t lo_wg = ptx::sw128_desc_lo(smem_a + OFF_WG);
       const uint32_t bar_a = smem_a + OFF_BAR;
-      constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_KVFULL = 32, B_KVEMPTY = 64, B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
+      constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_KVFULL = 32, B_KVEMPTY = 96, B_SFULL = 160, B_PFULL = 176, B_OFULL = 192, B_OFREE = 208;
       const uint32_t lo_q = ptx::sw128_desc_lo(smem_a + OFF_Q), lo_kv = ptx::sw128_desc_lo(smem_a + OFF_KV);
-      const uint32_t lo_p = ptx::sw128_desc_lo(smem_a + OFF_P);
       uint32_t gt0 = 0;   // global index (over this CTA's items) of the item's first K/V tile
       uint32_t ipar = 0;  // bit g: parity of the items group g has processed
       uint32_t tpar = 0;  // bit g: parity of the tiles group g has processed
@@ -375,26 +379,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
               if (!ptx::mbar_try_wait_a(bar_a + B_KVFULL + (gn % KV_STAGES) * 8, (gn / KV_STAGES) & 1)) continue;
             }
             ptx::tc_fence_after();
-            if (t + 1 < n_kv) {
-              issue_s(g, gt0 + t + 1);
-              if (t + 2 == n_kv) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);  // last S of the item: Q_g may be overwritten
-            }
             if (t == 0) {
               ptx::mbar_wait_a(bar_a + B_OFREE + g * 8, ((ipar >> g) & 1) ^ 1);  // previous item's O_g has been drained
               ptx::tc_fence_after();
             }
+            // O_g += P_g(t) V(t).  A: P as bf16 pairs in TMEM, inside the columns of S_g that its writer owned (keys
+            // 0..63 at columns 0..31, keys 64..127 at columns 64..95); B: V rows = keys (MN-major), 16 keys = 2048 bytes
             const uint32_t st = (gt0 + t) % KV_STAGES;
-            const uint32_t dp = lo_p + g * (2 * TILE_BYTES >> 4);
             const uint32_t dv = lo_kv + st * (2 * TILE_BYTES >> 4) + (TILE_BYTES >> 4);
 #pragma unroll
-            for (int ks = 0; ks < BKV / 16; ++ks) {
-              // A: P, K-major, two 64-key swizzle atoms 16 KB apart; B: V rows = keys (MN-major), 16 keys = 2048 bytes
-              const uint32_t da = dp + (ks >> 2) * (TILE_BYTES >> 4) + 2 * (ks & 3);
-              const uint32_t db = dv + ks * (2048 >> 4);
-              ptx::umma_bf16(tmem_base + 256 + g * 64, ptx::sw128_desc_from_lo(da), ptx::sw128_desc_from_lo(db), idesc_o,
-                             (t | ks) != 0 ? 1u : 0u);
-            }
+            for (int ks = 0; ks < BKV / 16; ++ks)
+              ptx::umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + g * 128 + (ks >> 2) * 64 + (ks & 3) * 8,
+                                ptx::sw128_desc_from_lo(dv + ks * (2048 >> 4)), idesc_o, (t | ks) != 0 ? 1u : 0u);
             ptx::umma_commit_a(bar_a + B_OFULL + g * 8);
+            // S_g(t+1) overwrites S_g(t) / P_g(t): the tensor pipe executes it after the PV above (same issuing thread)
+            if (t + 1 < n_kv) {
+              issue_s(g, gt0 + t + 1);
+              if (t + 2 == n_kv) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);  // last S of the item: Q_g may be overwritten
+            }
             done += 1u << (16 * g);
             tpar ^= 1u << g;
             // the stage of tile t is free once both groups' MMAs on it retire; the group that issues last commits
@@ -416,7 +418,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     const uint32_t tmem_s = tmem_base + g * 128, tmem_o = tmem_base + 256 + g * 64;
     const uint32_t tab_a = smem_a + OFF_TAB + g * TAB_BYTES;
     const uint32_t win_a = tab_a + TAB_WIN, mask_a = tab_a + TAB_MASK, pmax_a = tab_a + TAB_PMAX;
-    const uint32_t p_a = smem_a + OFF_P + g * 2 * TILE_BYTES + ch * TILE_BYTES + r * 128;
     const bool has_pad = a.key_pad != nullptr;
     const float qk_scale = 0.125f * LOG2E;  // head_dim^-0.5 (backbone.py:403), exp2 domain
     const int shift = (r + 1) & 3;          // which shifted window copy makes (c - r + 127 + shift) a multiple of 4
@@ -424,7 +425,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
     const int bar_id = 1 + g;
     // barrier addresses are derived from bar_a (32-bit shared address); par: bit 0 = item parity, bit 1 = tile parity
     const uint32_t bar_a = smem_a + OFF_BAR + g * 8;
-    constexpr uint32_t B_SFULL = 96, B_PFULL = 112, B_OFULL = 128, B_OFREE = 144;
+    constexpr uint32_t B_SFULL = 160, B_PFULL = 176, B_OFULL = 192, B_OFREE = 208;
     uint32_t par = 0;
 
     // table entries of a tile: thread stid < 255 owns entry stid of the bias window, thread stid < 128 one mask entry
@@ -519,16 +520,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
           const float ga = 1.0f / (1.0f + __expf(-za)), gb = 1.0f / (1.0f + __expf(-zb));
           gate = ga * (gb * grep_a - 1.0f) + 2.0f;
         }
-        if (t == jc_first / BKV) {  // finite: the chunk holds a valid key
-          const int c_first = jc_first % BKV;
-          const uint32_t ta = tmem_s + lane_addr + c_first, wa = wrow + (c_first - ch * 64) * 4;
-          const uint32_t ma = mask_a + (slot * BKV + c_first) * 4;
-          m_run = masked ? score_est<true>(ta, wa, ma, gate, qk_scale) : score_est<false>(ta, wa, ma, gate, qk_scale);
+        if (t == jc_first / BKV) {
+          // Reference estimate from a 16-key chunk that holds a valid key.  Both column halves of the row read the SAME
+          // chunk, and the other half's warp may already be writing P over its first 32 columns: only chunks in columns
+          // 32..63 / 96..127 of S (never covered by P) can be read by both; otherwise the owning half reads and shares.
+          int c = jc_first % BKV;
+          bool shared_est = false;
+          if (!(c & 32)) {
+            if (!masked || lds32(mask_a + (slot * BKV + 32) * 4) == 0.f) c = 32;
+            else if (lds32(mask_a + (slot * BKV + 96) * 4) == 0.f) c = 96;
+            else shared_est = true;
+          }
+          const uint32_t ta = tmem_s + lane_addr + c, wa = wrow + (c - ch * 64) * 4, ma = mask_a + (slot * BKV + c) * 4;
+          if (!shared_est || ch == (c >> 6))
+            m_run = masked ? score_est<true>(ta, wa, ma, gate, qk_scale) : score_est<false>(ta, wa, ma, gate, qk_scale);
+          if (shared_est) {  // group-uniform (the mask is per key)
+            if (ch == (c >> 6)) sts32(pmax_a + (768 + r) * 4, m_run);
+            named_bar_sync(bar_id, GROUP_THREADS);
+            m_run = lds32(pmax_a + (768 + r) * 4);
+          }
         }
-        if (t > 0) {
-          ptx::mbar_wait_a(bar_a + B_OFULL, slot ^ 1);  // PV(t-1) retired: O consistent, P buffer free
+        // O is only touched here when the reference moved (rare): S_g(t) is ordered after PV_g(t-1) on the tensor pipe, so
+        // P_g(t) may overwrite it without waiting for o_full
+        if (t > 0 && __any_sync(0xffffffffu, pending != 1.0f)) {
+          ptx::mbar_wait_a(bar_a + B_OFULL, slot ^ 1);  // PV(t-1) retired: O consistent
           ptx::tc_fence_after();
-          if (__any_sync(0xffffffffu, pending != 1.0f)) {
+          {
             l_run *= pending;
 #pragma unroll 1
             for (int hc = 0; hc < 2; ++hc) {
@@ -545,11 +562,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArg
         }
         const float m_eff = m_run == -INFINITY ? 0.f : m_run;  // -inf only while every key so far was masked (p = 0)
         float mx, sum;
-        if (masked) stream_tile<true>(taddr, wrow, mrow, gate, qk_scale, m_eff, p_a, r & 7, mx, sum);
-        else stream_tile<false>(taddr, wrow, mrow, gate, qk_scale, m_eff, p_a, r & 7, mx, sum);
+        if (masked) stream_tile<true>(taddr, wrow, mrow, gate, qk_scale, m_eff, mx, sum);
+        else stream_tile<false>(taddr, wrow, mrow, gate, qk_scale, m_eff, mx, sum);
         l_run += sum;
-        ptx::fence_proxy_async();  // generic-proxy writes of P -> visible to the tensor core's async proxy
-        ptx::tc_fence_before();
+        ptx::tc_fence_before();  // P is in TMEM (tcgen05.wait::st done): order it before the arrive
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_a(bar_a + B_PFULL);
         par ^= 2;
