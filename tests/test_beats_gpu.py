@@ -128,3 +128,24 @@ def test_batch_independence_and_full_size():
     # oracle on one clip of the big batch (CPU, ~10 s)
     orc = OE.beats_forward(W, wav[17:18].cpu().numpy(), None, OE.BeatsDims(layers=12))
     _cmp("10s clip vs oracle", one.cpu().numpy(), orc["x"])
+
+
+def test_long_clip_equals_short_clip_under_padding_mask():
+    """BASELINE config #5 shape (60 s clips, N = 2992 tokens), checked through a size-independent property instead of a
+    60 s oracle run: a 10 s clip followed by 50 s of padding (samples >= 992 frames * 160 masked, so tokens >= 496 are
+    padded) must give, on its first 496 tokens, the features of the 10 s clip alone -- padded tokens are zeroed before
+    the pos-conv (== its zero padding) and excluded as attention keys, and fbank / LayerNorm are per frame / per token."""
+    model, _ = _build(12, 3)
+    g = torch.Generator(device="cuda").manual_seed(77)
+    short = torch.randn(2, 160000, device="cuda", generator=g) * 0.1
+    long = torch.zeros(2, 960000, device="cuda")
+    long[:, :160000] = short
+    long[:, 160000:] = torch.randn(2, 800000, device="cuda", generator=g) * 0.1  # content under the mask must not matter
+    mask = torch.zeros(2, 960000, dtype=torch.bool, device="cuda")
+    mask[:, 992 * 160 :] = True
+    with torch.no_grad():
+        f_short = model(short)
+        f_long = model(long, mask)
+    assert f_short.shape == (2, 496, 768) and f_long.shape == (2, 2992, 768)
+    assert torch.isfinite(f_long).all()
+    _cmp("60 s masked vs 10 s", f_long[:, :496].cpu().numpy(), f_short.cpu().numpy())
