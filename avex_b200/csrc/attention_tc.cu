@@ -82,6 +82,16 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// the same barrier, returning the OR of `pred` over its threads
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(out)
+      : "r"((uint32_t)pred), "r"(id), "r"(nthreads)
+      : "memory");
+  return out != 0;
+}
 // explicit shared-space accesses (32-bit shared addresses): the carve-up below goes through an aligned byte offset, and
 // generic LD/ST on those pointers costs a long-scoreboard round trip
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -455,19 +465,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     };
     // The table slot of a tile is the parity of the group's running tile count (par bit 1), so slots alternate across item
     // boundaries too: the tables of the NEXT item's first tile are fetched and stored during the last tile of the current
-    // one (have_tab) and published by the barrier of the finalisation.
+    // one (have_tab) and published by the barrier of the finalisation.  Every barrier that publishes a tile's tables also
+    // ORs its `dead` flags: a tile without a padded / out-of-range key runs the unmasked fast path even when a padding
+    // mask was passed (the production pipeline always passes one; it is mostly false).
     bool have_tab = false;
+    bool tile_dead = false;  // the tile about to be processed holds a dead key (group-uniform)
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, npairs, a.H, N);
       if (g == 1 && !it.has_b) continue;
       const int q0 = it.q0 + g * BQ, b = it.b, h = it.h;
-      if (!have_tab) store_tables((par >> 1) & 1, fetch_bias(it, 0), fetch_dead(it, 0));
+      if (!have_tab) {
+        const bool dead0 = fetch_dead(it, 0);
+        store_tables((par >> 1) & 1, fetch_bias(it, 0), dead0);
+        tile_dead = named_bar_or(bar_id, GROUP_THREADS, dead0 && stid < BKV);  // tables of the first tile are visible
+      }
       const float grep_a = __ldg(a.grep_a + h);  // 12 floats: an L1/L2 hit, consumed after the first S wait
 
       // first tile that holds a valid key (0 unless the clip starts with >= 128 padded keys): group-uniform
       int jc_first = 0;  // first valid key rounded down to its 16-key chunk: tile = jc_first / 128, chunk column = jc_first % 128
-      if (has_pad) {
+      if (has_pad && a.key_pad[(size_t)b * N] != 0) {  // the clip STARTS with padding: find its first valid key
         const uint8_t* kpad = a.key_pad + (size_t)b * N;
         int jmin = N;
         for (int j = stid; j < N; j += GROUP_THREADS)
@@ -479,7 +496,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         jc_first = __float_as_int(lds32(pmax_a + 1024 * 4)) & ~15;  // tile == n_kv when every key is padded: no estimate
       }
 
-      if (!have_tab && !has_pad) named_bar_sync(bar_id, GROUP_THREADS);  // tables of the first tile are visible
       have_tab = false;
       float gate = 0.f;  // set on the item's first tile
 
@@ -487,8 +503,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       // (between tiles) when a tile's max exceeds it by more than RESCALE_THRESHOLD -- O and l are rescaled by
       // `pending` at the start of the next tile.  The result is exact after the final 1/l for any reference.
       float m_run = -INFINITY, l_run = 0.f, pending = 1.0f;
+      bool tab_dead = false;  // this thread's `dead` flag of the next item's first tile (stored on the last tile)
       for (int t = 0; t < n_kv; ++t) {
-        const bool masked = has_pad || (N - t * BKV < BKV);
+        const bool masked = tile_dead;
         const bool more = t + 1 < n_kv;
         float nbias = 0.f;
         bool ndead = false;
@@ -578,7 +595,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         if (more) {
           sts32(pmax_a + ((slot * 2 + ch) * 128 + r) * 4, mx);
           store_tables(slot ^ 1, nbias, ndead);
-          named_bar_sync(bar_id, GROUP_THREADS);
+          tile_dead = named_bar_or(bar_id, GROUP_THREADS, ndead && stid < BKV);
           const float m_tile = fmaxf(mx, lds32(pmax_a + ((slot * 2 + (ch ^ 1)) * 128 + r) * 4));
           if (m_run != -INFINITY && m_tile > m_run + RESCALE_THRESHOLD) {
             pending = ex2(m_run - m_tile);
@@ -586,12 +603,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           }
         } else if (have_tab) {
           store_tables(slot ^ 1, nbias, ndead);  // first tile of the next item; published by the barrier below
+          tab_dead = ndead;
         }
       }
 
       // ---- finalise: O / l -> bf16 -------------------------------------------------------------------------------
       sts32(pmax_a + (512 + ch * 128 + r) * 4, l_run);
-      named_bar_sync(bar_id, GROUP_THREADS);
+      tile_dead = named_bar_or(bar_id, GROUP_THREADS, have_tab && tab_dead && stid < BKV);  // next item's first tile, if stored
       const float l_tot = l_run + lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4);
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
       ptx::mbar_wait_a(bar_a + B_OFULL, ((par >> 1) & 1) ^ 1);
