@@ -224,13 +224,15 @@ def run_ours(args):
         """pinned host batch -> H2D (copy stream, double-buffered) -> forward -> D2H of the pooled embeddings."""
         cur = i & 1
         main = torch.cuda.current_stream()
-        main.wait_event(ev_ready[cur])  # this batch has landed in HBM
-        res = bk.run(dev_in[cur], None, want_features=False, want_pooled=True)
-        ev_consumed[cur].record(main)
-        with torch.cuda.stream(copy_stream):  # next batch's H2D overlaps this batch's compute
+        # the next batch's H2D is enqueued BEFORE this batch's 69 kernels, so that it overlaps them (enqueued after, the copy
+        # started late and 2.9 ms of the 3.0 ms transfer showed up in the step: tools/e2e_probe.py)
+        with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_consumed[cur ^ 1])  # the forward that last read that buffer has finished
             dev_in[cur ^ 1].copy_(host[cur ^ 1], non_blocking=True)
             ev_ready[cur ^ 1].record(copy_stream)
+        main.wait_event(ev_ready[cur])  # this batch has landed in HBM
+        res = bk.run(dev_in[cur], None, want_features=False, want_pooled=True)
+        ev_consumed[cur].record(main)
         if world > 1:
             dist.all_gather_into_tensor(gathered, res["pooled"])
         pooled_host.copy_(res["pooled"], non_blocking=True)
