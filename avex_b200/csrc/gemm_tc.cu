@@ -133,6 +133,9 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -140,7 +143,8 @@ __device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c
 template <int MODE, bool PAIR, int EW, bool DEEPK>
 __global__ void __launch_bounds__(32 * (CTRL_WARPS + EW), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_y, const GemmArgs g) {
+                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_y,
+                 const __grid_constant__ CUtensorMap map_xb, const GemmArgs g) {
   using C = Cfg<PAIR, EW, MODE, DEEPK>;
   constexpr int RES_DEPTH = C::RES_DEPTH;
   constexpr int STAGES = C::STAGES, EPI_WARPS = C::EPI_WARPS, EPI_THREADS = C::EPI_THREADS, CHUNKS = C::CHUNKS;
@@ -179,6 +183,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ptx::prefetch_tensormap(&map_b);
     if (MODE == MODE_RES) ptx::prefetch_tensormap(&map_res);
     if (MODE != MODE_CONV) ptx::prefetch_tensormap(&map_y);
+    if (MODE == MODE_RES && g.ln_out_bf16 != nullptr) ptx::prefetch_tensormap(&map_xb);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -311,6 +316,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int mu, nb;
       if (!has_res || lane != 0 || !tile_of(n >> 2, mu, nb)) return;
       const int s = n % RES_DEPTH;
+      // the slot of a tile's last box doubles as the bf16 staging of its LayerNorm pass: that store must have left it
+      if (ln && (n & 3) == RES_DEPTH - 1) ptx::tma_store_wait_read();
       ptx::fence_proxy_async();  // the generic-proxy reads of this slot are ordered before the async-proxy overwrite
       ptx::mbar_arrive_expect_tx(&rbar[s], STG_BYTES_PER_WARP);
       ptx::tma_load_2d_s(rbuf + s * STG_BYTES_PER_WARP, &map_res, &rbar[s], nb * BN + (half * 4 + (n & 3)) * 32,
@@ -440,6 +447,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         // ---- pass 2: y = (v - mean) * rstd * gamma + beta ----------------------------------------------------
+        const uint32_t xbuf = rbuf + ((it * 4 + 3) % RES_DEPTH) * STG_BYTES_PER_WARP;  // free until the next tile's first box
 #pragma unroll 1
         for (int ci = 0; ci < 4; ++ci) {
           const int col0 = nb * BN + (half * 4 + ci) * 32;
@@ -464,14 +472,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             y[4 * j + 2] = fmaf((__uint_as_float(r[4 * j + 2]) - mean) * rstd, ga.z, be.z);
             y[4 * j + 3] = fmaf((__uint_as_float(r[4 * j + 3]) - mean) * rstd, ga.w, be.w);
           }
-          if (g.ln_out_bf16 != nullptr && row_ok) {  // 64 contiguous bytes per row: two full sectors
-            uint4* dst = reinterpret_cast<uint4*>(g.ln_out_bf16 + (size_t)grow * LN_C + col0);
+          // Both outputs leave through TMA: the fp32 box from the warp's staging buffer, the bf16 box (32 rows x 64 bytes,
+          // 64-byte swizzle) from the residual-ring slot that the tile's last box has just vacated.  (Per-thread 16-byte
+          // stores of the bf16 rows -- 32 scattered lines per instruction -- cost 0.09 ms of the 0.31 ms out_proj launch.)
+          if (lane == 0) ptx::tma_store_wait_read();  // the previous boxes have left both staging buffers
+          __syncwarp();
+          if (g.ln_out_bf16 != nullptr) {
+            const uint32_t sw64 = (lane >> 1) & 3;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              __stcs(dst + j, make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
-                                         pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7])));
+              sts128u(xbuf + lane * 64 + ((j ^ sw64) << 4), pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
+                      pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
           }
-          if (g.ln_out_f32 != nullptr) store_box(y, col0, row0);
+          if (g.ln_out_f32 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128f(ybuf + rowoff + ((j ^ sw) << 4), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          }
+          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0) {  // rows >= M are clipped by the tensor maps
+            if (g.ln_out_bf16 != nullptr) ptx::tma_store_2d_s(&map_xb, xbuf, col0, row0);
+            if (g.ln_out_f32 != nullptr) ptx::tma_store_2d_s(&map_y, ybuf, col0, row0);
+            ptx::tma_store_commit();
+          }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -721,6 +744,7 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
     attr_set = true;
   }
   CUtensorMap ma, mb;
+  CUtensorMap mxb{};  // bf16 output of the fused LayerNorm epilogue (MODE_RES)
   int rc = make_tmap_2d_bf16(&ma, A, g.M, g.K, lda, BM, BK);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&mb, W, g.N, g.K, ldw, C::B_ROWS, BK);
@@ -733,6 +757,10 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
   if (MODE == MODE_RES) {
     if (g.residual != nullptr) {
       rc = make_tmap_2d_f32(&mres, g.residual, g.M, g.N, g.N, 32);
+      if (rc) return rc;
+    }
+    if (g.ln_gamma != nullptr && g.ln_out_bf16 != nullptr) {
+      rc = make_tmap_2d_64B(&mxb, g.ln_out_bf16, g.M, g.N, g.N, 2, 32);
       if (rc) return rc;
     }
     float* y = g.ln_gamma != nullptr ? g.ln_out_f32 : reinterpret_cast<float*>(g.out);
@@ -759,9 +787,9 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, ma, mb, mres, my, g));
+    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, ma, mb, mres, my, mxb, g));
   } else {
-    gemm_bf16_kernel<MODE, PAIR, EW, DEEPK><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, mres, my, g);
+    gemm_bf16_kernel<MODE, PAIR, EW, DEEPK><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, mres, my, mxb, g);
   }
   prof_end(st);
   AVEXK_LAUNCH_CHECK();

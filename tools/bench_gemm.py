@@ -37,7 +37,8 @@ def main():
             def run():
                 if ln:
                     rc = lib.avexk_gemm_bf16_ln(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), None, R.data_ptr(), 2.2133638,
-                                                gam.data_ptr(), bet.data_ptr(), 1e-5, out.data_ptr(), xb.data_ptr(), scratch.data_ptr(), nb, st)
+                                                gam.data_ptr(), bet.data_ptr(), 1e-5, None if os.environ.get("GEMM_NOF32") else out.data_ptr(),
+                                                None if os.environ.get("GEMM_NOXB") else xb.data_ptr(), scratch.data_ptr(), nb, st)
                 else:
                     rc = lib.avexk_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), gelu, None,
                                              R.data_ptr() if res else None, 2.2133638, out.data_ptr(), N, int(obf), st)
