@@ -255,6 +255,54 @@ def test_attention_reference_lags_row_max(lib):
         assert torch.nn.functional.cosine_similarity(out.float().flatten(), ref.flatten(), dim=0).item() >= 0.9995
 
 
+def test_attention_random_shapes_and_masks(lib):
+    """Seeded sweep over ragged shapes and mask patterns (none / suffix / prefix / scattered / a fully padded clip): every
+    tile-boundary case of the kernel -- single-tile pairs, a second query tile with a few rows, first valid key in any
+    16-key chunk (own-half, shared and safe-chunk estimates), masks that leave whole tiles dead."""
+    rng = np.random.RandomState(2024)
+    worst = 0.0
+    for case in range(48):
+        N = int(rng.choice([1, 7, 16, 17, 63, 64, 65, 120, 128, 129, 130, 200, 255, 256, 257, 300, 383, 384, 385, 500, 513, 640]))
+        B, H = int(rng.randint(1, 4)), int(rng.randint(1, 4))
+        kind = ["none", "suffix", "prefix", "scatter", "deadclip"][case % 5]
+        g = torch.Generator(device="cuda").manual_seed(1000 + case)
+        qkv = (torch.randn(B * N, 3 * H * 64, device="cuda", generator=g) * (1.0 + (case % 3))).to(torch.bfloat16)
+        gw = torch.randn(2, 64, device="cuda", generator=g) * 0.2
+        gb = torch.randn(2, device="cuda", generator=g) * 0.2
+        ga = 1.0 + 0.2 * torch.randn(H, device="cuda", generator=g)
+        table = torch.randn(320, H, generator=torch.Generator().manual_seed(case)) * 2.0
+        bias_vec = torch.from_numpy(OR.bias_vector(table.numpy(), N)).cuda()
+        key_pad = None
+        if kind != "none":
+            kp = np.zeros((B, N), np.uint8)
+            for b in range(B):
+                if kind == "suffix":
+                    kp[b, rng.randint(1, N + 1):] = 1
+                elif kind == "prefix":
+                    kp[b, : rng.randint(0, N)] = 1
+                elif kind == "scatter":
+                    kp[b] = rng.rand(N) < 0.6
+                    kp[b, rng.randint(0, N)] = 0  # at least one valid key
+            if kind == "deadclip":
+                kp[0, :] = 1
+            key_pad = torch.from_numpy(kp).cuda()
+        out = torch.full((B * N, H * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        _check(lib.avexk_attention_gated(qkv.data_ptr(), B, N, H, gw.data_ptr(), gb.data_ptr(), ga.data_ptr(), bias_vec.data_ptr(),
+                                         key_pad.data_ptr() if key_pad is not None else None, out.data_ptr(), _stream()), lib)  # fmt: skip
+        ref = _attn_ref(qkv, B, N, H, gw, gb, ga, bias_vec, key_pad)
+        o = out.float()
+        assert torch.isfinite(o).all(), (case, N, B, H, kind)
+        live = torch.ones(B, dtype=torch.bool, device="cuda") if key_pad is None else ~(key_pad.bool().all(dim=1))
+        rows = live[:, None].expand(B, N).reshape(-1)
+        if (~rows).any():  # a clip without a valid key: the reference softmax is NaN there, the kernel returns zeros
+            assert (o[~rows] == 0).all(), (case, N, kind)
+        err = (o[rows] - ref[rows]).abs().max().item() if rows.any() else 0.0
+        scale = max(1.0, ref[rows].abs().max().item()) if rows.any() else 1.0
+        assert err <= 2e-2 * scale, (case, N, B, H, kind, err)
+        worst = max(worst, err / scale)
+    print("attention sweep: worst relative max-abs error %.3e" % worst)
+
+
 @pytest.mark.parametrize("B,N,pad", [(2, 48, False), (1, 248, False), (2, 131, True), (3, 496, False)])
 def test_posconv(lib, B, N, pad):
     dims = OE.BeatsDims()
