@@ -110,7 +110,9 @@ int avexk_layernorm(const float* x, int M, int C, const float* gamma, const floa
  * gate_w [2,64], gate_b [2]: grep_linear rows pre-summed in groups of four (backbone.py:547-549);
  * grep_a [H]; bias_vec [H, 2N-1] with bias_vec[h, (j-i)+N-1] = table[bucket(j-i), h] (backbone.py:475-492);
  * key_pad [B,N] bytes (1 = padded key -> -inf) or NULL.  out [B*N, H*64] bf16 (token-major, ready for out_proj).
- *   out_i = softmax_j(q_i.k_j / 8 + gate_i * bias[h, j-i] + pad_j) . v_j,  gate from UNscaled q. */
+ *   out_i = softmax_j(q_i.k_j / 8 + gate_i * bias[h, j-i] + pad_j) . v_j,  gate from UNscaled q.
+ * Rows of a clip whose keys are ALL padded come out as zeros (the reference's softmax is NaN there).  The gate logits are
+ * formed on the tensor core with gate_w split into bf16 hi + lo parts (~16 mantissa bits). */
 int avexk_attention_gated(const void* qkv, int B, int N, int H, const float* gate_w, const float* gate_b,
                           const float* grep_a, const float* bias_vec, const uint8_t* key_pad, void* out, void* stream);
 
