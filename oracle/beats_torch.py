@@ -37,13 +37,13 @@ def beats_forward(Wt: dict, wav: torch.Tensor, padding_mask=None, dims: BeatsDim
     from . import kaldi_fbank as OF
 
     if tables is None:
-        tables = (torch.from_numpy(OF.povey_window()), torch.from_numpy(OF.mel_filterbank()))
+        tables = (torch.from_numpy(OF.povey_window()).to(wav.device), torch.from_numpy(OF.mel_filterbank()).to(wav.device))
     g = lambda n: Wt[n]  # noqa: E731
     fb = fbank(wav.float() * 2**15, *tables)
     fb = (fb - dims.fbank_mean) / (2 * dims.fbank_std)  # beats.py:323
     key_pad = None
     if padding_mask is not None:
-        key_pad = torch.from_numpy(token_padding_mask(np.asarray(padding_mask, dtype=bool), dims))
+        key_pad = torch.from_numpy(token_padding_mask(np.asarray(padding_mask.cpu() if torch.is_tensor(padding_mask) else padding_mask, dtype=bool), dims)).to(wav.device)
     x = F.conv2d(fb.unsqueeze(1), g("backbone.patch_embedding.weight"), stride=16)  # beats.py:349-350
     x = x.reshape(x.shape[0], x.shape[1], -1).transpose(1, 2)
     x = F.layer_norm(x, (dims.patch_embed,), g("backbone.layer_norm.weight"), g("backbone.layer_norm.bias"))
@@ -61,8 +61,10 @@ def beats_forward(Wt: dict, wav: torch.Tensor, padding_mask=None, dims: BeatsDim
     x = F.layer_norm(x, (C,), g("backbone.encoder.layer_norm.weight"), g("backbone.encoder.layer_norm.bias"))
     H, d = dims.heads, C // dims.heads
     table = g("backbone.encoder.layers.0.self_attn.relative_attention_bias.weight")
-    bv = torch.from_numpy(bias_vector(table.numpy(), N, dims.num_buckets, dims.max_distance))
-    idx = (torch.arange(N)[None, :] - torch.arange(N)[:, None]) + (N - 1)
+    dev = x.device  # CPU for the baseline; tools/bench_eager_gpu.py runs the same op mix on the GPU
+    bv = torch.from_numpy(bias_vector(table.cpu().numpy(), N, dims.num_buckets, dims.max_distance)).to(dev)
+    ar = torch.arange(N, device=dev)
+    idx = (ar[None, :] - ar[:, None]) + (N - 1)
     pos_bias = bv[:, idx].unsqueeze(0).expand(B, -1, -1, -1)  # [B,H,N,N], backbone.py:526-528
     alpha = dims.alpha
     for li in range(dims.layers):
@@ -74,7 +76,7 @@ def beats_forward(Wt: dict, wav: torch.Tensor, padding_mask=None, dims: BeatsDim
         ga, gb = torch.sigmoid(F.linear(q, g(sa + ".grep_linear.weight"), g(sa + ".grep_linear.bias")).view(B, H, N, 2, 4).sum(-1)).chunk(2, dim=-1)
         mask = (ga * (gb * g(sa + ".grep_a") - 1.0) + 2.0) * pos_bias  # materialised, like the reference (backbone.py:551)
         if key_pad is not None:
-            pm = torch.zeros(B, 1, 1, N)
+            pm = torch.zeros(B, 1, 1, N, device=dev)
             pm.masked_fill_(key_pad[:, None, None, :], float("-inf"))
             mask = mask + pm
         a = F.scaled_dot_product_attention(q, k, vv, attn_mask=mask, scale=d**-0.5)
