@@ -66,6 +66,7 @@ static_assert(SMEM_BYTES <= 232448, "attention_tc: shared memory budget");
 
 struct AttnTcArgs {
   int B, N, H;
+  int n_items;             // B * H * ceil(N / 256): read from the constant bank where needed (a register-resident copy spilled)
   const float* gate_w;     // [2,64]
   const float* gate_b;     // [2]
   const float* grep_a;     // [H]
@@ -262,7 +263,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   const int N = a.N;
   const int n_kv = (N + BKV - 1) / BKV;
   const int npairs = (N + 2 * BQ - 1) / (2 * BQ);
-  const int n_items = a.B * a.H * npairs;
+  const int n_items = a.n_items;
 
   // Gate weights -> a 16-row UMMA B operand, once per CTA: rows 0,1 = bf16(w), rows 2,3 = bf16(w - hi) (the two halves
   // are summed after the MMA, so the gate logits carry ~16 mantissa bits of w), rows 4..15 = 0.
@@ -405,7 +406,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             for (int ks = 0; ks < BKV / 16; ++ks)
               ptx::umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + g * 128 + (ks >> 2) * 64 + (ks & 3) * 8,
                                 ptx::sw128_desc_from_lo(dv + ks * (2048 >> 4)), idesc_o, (t | ks) != 0 ? 1u : 0u);
-            ptx::umma_commit_a(bar_a + B_OFULL + g * 8);
+            if (t + 1 == n_kv) ptx::umma_commit_a(bar_a + B_OFULL + g * 8);  // the item's O_g is complete (one phase per item)
             // S_g(t+1) overwrites S_g(t) / P_g(t): the tensor pipe executes it after the PV above (same issuing thread)
             if (t + 1 < n_kv) {
               issue_s(g, gt0 + t + 1);
@@ -561,11 +562,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
             m_run = lds32(pmax_a + (768 + r) * 4);
           }
         }
-        // O is only touched here when the reference moved (rare): S_g(t) is ordered after PV_g(t-1) on the tensor pipe, so
-        // P_g(t) may overwrite it without waiting for o_full
+        // O is only touched here when the reference moved (rare).  No barrier is needed: S_g(t) was issued after PV_g(t-1)
+        // and its commit (s_full, waited for above) covers every earlier MMA of the issuing thread, so O is consistent.
         if (t > 0 && __any_sync(0xffffffffu, pending != 1.0f)) {
-          ptx::mbar_wait_a(bar_a + B_OFULL, slot ^ 1);  // PV(t-1) retired: O consistent
-          ptx::tc_fence_after();
           {
             l_run *= pending;
 #pragma unroll 1
@@ -612,7 +611,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       tile_dead = named_bar_or(bar_id, GROUP_THREADS, have_tab && tab_dead && stid < BKV);  // next item's first tile, if stored
       const float l_tot = l_run + lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4);
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-      ptx::mbar_wait_a(bar_a + B_OFULL, ((par >> 1) & 1) ^ 1);
+      ptx::mbar_wait_a(bar_a + B_OFULL, par & 1);  // the item's last PV has retired
       ptx::tc_fence_after();
       uint32_t o[32];
       ptx::tmem_ld_32x32(tmem_o + lane_addr + ch * 32, o);
@@ -690,8 +689,9 @@ extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const
   CUtensorMap map_out;  // out as [B*N, H*64] bf16, 32-row x 64-byte boxes (one softmax warp's share of an O tile)
   rc = make_tmap_2d_64B(&map_out, out, (long long)B * N, (long long)H * HD, (long long)H * HD, 2, 32);
   if (rc) return rc;
-  AttnTcArgs a{B, N, H, gate_w, gate_b, grep_a, bias_vec, key_pad, reinterpret_cast<__nv_bfloat16*>(out)};
   const long long items = (long long)B * H * ceil_div(N, 2 * BQ);
+  AVEXK_CHECK_ARG(items < (1LL << 31), "avexk_attention_gated: too many work items");
+  AttnTcArgs a{B, N, H, (int)items, gate_w, gate_b, grep_a, bias_vec, key_pad, reinterpret_cast<__nv_bfloat16*>(out)};
   const int grid = (int)(items < num_sms() ? items : num_sms());
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   prof_begin(st, KID_ATTN, 4.0 * B * H * (double)N * N * HD);
