@@ -57,10 +57,13 @@ struct Cfg {
   static constexpr int KSUB = (MODE == MODE_PLAIN || MODE == MODE_GELU) ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2, SUB_BYTES = A_BYTES + B_BYTES, STAGE_BYTES = KSUB * SUB_BYTES;
   // MODE_RES spends 96 KB of shared memory on the residual ring, so it keeps fewer operand stages
-  static constexpr int RES_DEPTH = (PAIR && DEEPK) ? 2 : 3;  // residual boxes in flight per epilogue warp (MODE_RES)
+  // residual boxes in flight per epilogue warp (MODE_RES).  DEEPK: a tile's 48 k-blocks hide the whole epilogue, so the
+  // residual is fetched box by box without prefetch and the ring's shared memory goes to a FIFTH operand stage (fc2+LN:
+  // 3 stages 0.585 ms, 4 stages 0.549 ms -- the DRAM-sourced A rows need the depth)
+  static constexpr int RES_DEPTH = (PAIR && DEEPK) ? 1 : 3;
   // per-warp output staging: 32 rows x 64 bytes for the bias / GELU epilogue, 32 x 128 bytes for the others
   static constexpr int STG_BYTES = (MODE == MODE_PLAIN || MODE == MODE_GELU) ? STG_BYTES_PER_WARP / 2 : STG_BYTES_PER_WARP;
-  static constexpr int STAGES = MODE == MODE_RES ? (PAIR ? (DEEPK ? 4 : 3) : 2) : MODE == MODE_CONV ? (PAIR ? 5 : 3) : (PAIR ? 3 : 2);
+  static constexpr int STAGES = MODE == MODE_RES ? (PAIR ? (DEEPK ? 5 : 3) : 2) : MODE == MODE_CONV ? (PAIR ? 5 : 3) : (PAIR ? 3 : 2);
   static constexpr int TX_SUB = SUB_BYTES * (PAIR ? 2 : 1);  // bytes landing on the (leader's) full barrier per k-block
   static constexpr int UM = PAIR ? 2 * BM : BM;                  // output rows per scheduling unit
   static constexpr int RES_BYTES = MODE == MODE_RES ? EW * RES_DEPTH * STG_BYTES_PER_WARP : 0;
