@@ -58,6 +58,7 @@ _vp, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 SIGNATURES = {
     "avexk_last_error": (C.c_char_p, []),
     "avexk_version": (_i, []),
+    "avexk_build_id": (C.c_char_p, []),
     "avexk_launch_count": (_ll, []),
     "avexk_profile_enable": (None, [_i]),
     "avexk_profile_read": (_i, [_i, C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -143,6 +144,17 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    # a stale binary must never be what runs: the .so is git-ignored and travels with the snapshot, so compare the id compiled
+    # into it with the hash of the sources lying next to it (skipped only when the sources are not shipped at all)
+    from . import build as _build
+
+    if os.path.isdir(_build.CSRC):
+        want, got = _build.source_id(), lib.avexk_build_id().decode()
+        if want != got:
+            raise AvexkError(
+                f"{LIB_PATH} is stale: built from sources {got}, the tree hashes to {want}. "
+                "Rebuild with `python -m avex_b200.build`."
+            )
     _lib = lib
     return lib
 

@@ -110,6 +110,19 @@ def relative_bias_vector(table: torch.Tensor, n_tokens: int, num_buckets: int, m
     return table.detach().float()[idx].t().contiguous()
 
 
+def call_forward_hooks(mod: nn.Module, out):
+    """Fire `mod`'s forward hooks as `nn.Module._call_impl` would after a forward that produced `out` (positional inputs are
+    not available: the fused kernels never materialise them).  Hooks registered `with_kwargs=True` get the 4-argument form."""
+    for hid, hook in list(mod._forward_hooks.items()):
+        if hid in getattr(mod, "_forward_hooks_with_kwargs", {}):
+            r = hook(mod, (), {}, out)
+        else:
+            r = hook(mod, (), out)
+        if r is not None:
+            out = r
+    return out
+
+
 def forward_padding_mask(n_feat: int, mask: torch.Tensor) -> torch.Tensor:
     """beats.py:283-302."""
     extra = mask.size(1) % n_feat
@@ -206,7 +219,36 @@ class BEATs(nn.Module):
 
     # ---- engine management ------------------------------------------------------------------------------------
     def _weight_version(self):
+        """(storage, autograd version) per parameter.  In-place writes through `.data` (as the reference's own init does with
+        `.data.copy_`) do NOT bump `_version`: call `invalidate()` after such an update."""
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate(self) -> None:
+        """Drop the packed bf16 weight copies and cached bias vectors; the next forward re-packs from the parameters."""
+        self.release()
+        self._bias_cache.clear()
+
+    refresh_weights = invalidate
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)  # copies in place under no_grad: versions may not change
+        self.invalidate()
+        return out
+
+    # native handles are per process: copies / pickles carry parameters only and rebuild lazily
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"], st["_engine_key"], st["_ws"], st["_bias_cache"] = None, None, None, {}
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     def _ensure_engine(self, device: torch.device):
         key = (device, self._weight_version(), self.precision)
@@ -340,8 +382,6 @@ class BEATs(nn.Module):
             hooks[li] = torch.empty((B, N, Cdim), device=device, dtype=torch.float32)
             hook_ptrs[li] = hooks[li].data_ptr()
         bias_vec = self._bias_vec(N, device)
-        # masked mean only when some token is padded (beats_model.py:269); decided on the host
-        pool_mask = key_pad if (key_pad is not None and want_pooled and bool(tok_mask.any())) else None
         with torch.cuda.device(device):
             rc = lib.avexk_beats_forward(
                 engine, x.data_ptr(), B, T, x.stride(0) if B > 1 else max(T, x.stride(0)), self.fbank.handle(device),
@@ -351,8 +391,6 @@ class BEATs(nn.Module):
                 self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream(device).cuda_stream,
             )  # fmt: skip
         _lib.check(rc, "avexk_beats_forward")
-        if want_pooled and key_pad is not None and pool_mask is None:
-            pass  # all-False mask: kernel already used the plain mean
         return {"features": feats, "pooled": pooled, "hooks": hooks, "padding_mask": tok_mask}
 
     def _fire_hooks(self, hooks: dict) -> None:
@@ -360,10 +398,7 @@ class BEATs(nn.Module):
         for li, t in hooks.items():
             mod = self.post_extract_proj if li == 0 else self.encoder.layers[li - 1].fc2
             out = t if li == 0 else t.transpose(0, 1)  # blocks run (T,B,C) in the reference, backbone.py:182
-            for hook in list(mod._forward_hooks.values()):
-                r = hook(mod, (), out)
-                if r is not None:
-                    out = r
+            out = call_forward_hooks(mod, out)
 
     def _hooked_layers(self) -> list[int]:
         idx = []

@@ -6,6 +6,7 @@ The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -31,6 +32,41 @@ def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def tracked_files() -> list[str]:
+    """Every file the binary is built from: csrc/*.cu, csrc/*.cuh, include/avexk.h."""
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "avexk.h"))
+    return sorted(files)
+
+
+def source_id() -> str:
+    """sha256 over the tracked sources (name + contents).  Compiled into libavexk.so (`avexk_build_id()`), so that a stale
+    binary -- the .so is git-ignored and ships with the gpurun snapshot -- can never be what the tests load."""
+    h = hashlib.sha256()
+    for f in tracked_files():
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+        h.update(b"\0")
+    return h.hexdigest()[:32]
+
+
+_MARK = b"AVEXK_BUILD_ID="
+
+
+def binary_id(path: str = LIB) -> str | None:
+    """The id compiled into an existing libavexk.so, read from its bytes (no dlopen), or None."""
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as fh:
+        blob = fh.read()
+    i = blob.find(_MARK)
+    if i < 0:
+        return None
+    j = i + len(_MARK)
+    return blob[j : j + 32].decode("ascii", "replace")
+
+
 def _stale(target: str, deps: list[str]) -> bool:
     if not os.path.exists(target):
         return True
@@ -46,13 +82,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in FLAGS if f != "--use_fast_math=false"]
     if verbose:
         flags += ["-Xptxas", "-v"]
+    sid = source_id()
+    if binary_id() != sid:
+        force = True  # sources differ from what the shipped binary was built from (mtimes cannot be trusted after a snapshot)
     jobs = []
     objs = []
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc, *ARCH, *flags, "-c", src, "-o", obj])
+            extra = [f'-DAVEXK_BUILD_ID_STR="{sid}"'] if os.path.basename(src) == "api.cu" else []
+            jobs.append([nvcc, *ARCH, *flags, *extra, "-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,6 +107,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(log)
     if jobs or force or _stale(LIB, objs):
         run([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"])
+    got = binary_id()
+    if got != sid:
+        raise RuntimeError(f"libavexk.so carries build id {got}, sources hash to {sid}")
     return LIB
 
 

@@ -41,6 +41,12 @@ void prof_end(cudaStream_t st) {
   cudaEventRecord(g_prof.back().b, st);
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -56,7 +62,13 @@ int num_sms() {
 }  // namespace avexk
 
 extern "C" const char* avexk_last_error(void) { return avexk::g_err; }
-extern "C" int avexk_version(void) { return 100; }
+extern "C" int avexk_version(void) { return 200; }
+#ifndef AVEXK_BUILD_ID_STR
+#define AVEXK_BUILD_ID_STR "unset"
+#endif
+// sha256 prefix of csrc/*.cu{,h} + include/avexk.h at build time (avex_b200/build.py); the marker makes it greppable in the file.
+static const char g_build_id[] = "AVEXK_BUILD_ID=" AVEXK_BUILD_ID_STR;
+extern "C" const char* avexk_build_id(void) { return g_build_id + 15; }
 extern "C" long long avexk_launch_count(void) { return avexk::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" void avexk_profile_enable(int on) {

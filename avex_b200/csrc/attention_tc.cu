@@ -676,10 +676,11 @@ extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const
   AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   "avexk_attention_gated: qkv/out must be 16-byte aligned");
   if (B == 0) return AVEXK_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     AVEXK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   // qkv viewed as [B][N][3*H*64]: rows past the end of a clip are out of bounds -> zero-filled by TMA
   CUtensorMap map;

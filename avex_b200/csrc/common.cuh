@@ -43,6 +43,7 @@ void count_launch(int n = 1);
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();
+int current_device();  // clamped to [0, 64)
 
 // kernel ids of the optional event profiler (avexk_profile_*)
 enum { KID_FBANK = 0, KID_GEMM = 1, KID_ATTN = 2, KID_LAYERNORM = 3, KID_POSCONV = 4, KID_OTHER = 5 };

@@ -225,10 +225,11 @@ int launch_posconv_fp32(const float* x0, const float* Wf, const float* bias, flo
   AVEXK_CHECK_ARG(B <= 65535, "posconv_fp32: B=%d exceeds grid.z", B);
   if (B == 0 || N == 0) return AVEXK_OK;
   const int smem = ((PT + PTAPS - 1) * PCG + PCHUNK * PCG * PCG) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     AVEXK_CUDA(cudaFuncSetAttribute(posconv_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid(ceil_div(N, PT), G, B);
   prof_begin(st, KID_POSCONV, 2.0 * B * N * (double)(G * cg) * cg * taps);

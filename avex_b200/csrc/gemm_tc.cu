@@ -741,10 +741,11 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
   constexpr int EW = MODE == MODE_RES ? 8 : 16;
   using C = Cfg<PAIR, EW, MODE, DEEPK>;
   constexpr int NTHREADS = C::NTHREADS;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     AVEXK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   CUtensorMap ma, mb;
   CUtensorMap mxb{};  // bf16 output of the fused LayerNorm epilogue (MODE_RES)

@@ -277,10 +277,11 @@ int launch_posconv(const __nv_bfloat16* xg, const __nv_bfloat16* Wpc, const floa
                    int N, int G, int cg, int taps, cudaStream_t st) {
   AVEXK_CHECK_ARG(cg == CG && taps == TAPS, "posconv kernel is specialised to 48 channels/group and 128 taps (got %d, %d)", cg, taps);
   if (B == 0 || N == 0) return AVEXK_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: the opt-in is a per-device function attribute
+  const int dev_ = current_device();
+  if (!attr_set[dev_]) {
     AVEXK_CUDA(cudaFuncSetAttribute(posconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   CUtensorMap mx, mw;
   int rc = make_tmap_3d_bf16(&mx, xg, (long long)G * 64, N, B, (long long)G * 64, (long long)N * G * 64, 64, 128, 1, true);

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .beats import call_forward_hooks
 from .melspec import N_MELS, MelSpectrogram
 
 
@@ -95,6 +96,15 @@ class EfficientNetEngine:
         self._engine, self._engine_key = h, key
         return h
 
+    def invalidate(self) -> None:
+        """Drop the packed weights (needed after in-place `.data` updates, which do not bump tensor versions)."""
+        self.release()
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"], st["_engine_key"], st["_ws"] = None, None, None
+        return st
+
     def release(self) -> None:
         if self._engine is not None:
             _lib.load().avexk_effnet_destroy(self._engine)
@@ -114,11 +124,7 @@ class EfficientNetEngine:
     def fire_hooks(self, hooks: dict) -> None:
         for i, t in hooks.items():
             mod = self.hook_modules[i]
-            out = t
-            for hook in list(mod._forward_hooks.values()):
-                r = hook(mod, (), out)
-                if r is not None:
-                    out = r
+            call_forward_hooks(mod, t)
 
     def run(self, image: torch.Tensor, minmax: Optional[torch.Tensor], *, want_features: bool = True, want_logits: bool = False,
             hook_layers: Optional[list[int]] = None) -> dict:

@@ -98,6 +98,21 @@ class KaldiFbank(nn.Module):
         except Exception:
             pass
 
+    # the native handle is per process / device: copies and pickles carry the buffers only and re-create it lazily
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_handle"], st["_handle_device"] = None, None
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def num_frames(self, num_samples: int) -> int:
         return 0 if num_samples < self.win_length else 1 + (num_samples - self.win_length) // self.hop_length
 

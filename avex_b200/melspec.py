@@ -52,6 +52,11 @@ class MelSpectrogram:
         except Exception:
             pass
 
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_handle"], st["_handle_device"] = None, None
+        return st
+
     @staticmethod
     def num_frames(num_samples: int) -> int:
         return 1 + num_samples // HOP

@@ -22,6 +22,8 @@ class AudioProcessor:
         self._mel = None
 
     def __call__(self, waveform: torch.Tensor) -> torch.Tensor:
+        if waveform.dim() == 1:
+            waveform = waveform.unsqueeze(0)  # audio_utils.py:126-128: [T] -> [1, T]
         if self.representation == "raw":
             return waveform
         if self.representation == "mel_spectrogram" and (self.n_fft, self.hop_length, self.win_length, self.n_mels) == (800, 160, 800, 128):

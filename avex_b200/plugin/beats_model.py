@@ -79,6 +79,28 @@ def make_model_class(base):
                     if n.endswith("post_extract_proj") or (n.endswith(".fc2") and "backbone.encoder.layers." in n)
                 ]
 
+        def servable_layers(self) -> List[str]:
+            """Layers whose forward hooks the fused forward can feed: the tensors the kernels materialise."""
+            self._discover_embedding_layers()
+            return list(self._layer_names)
+
+        def register_hooks_for_layers(self, target_layers) -> List[str]:
+            """base_model.py:101-200, restricted to the layers the fused kernels materialise.  The reference accepts any
+            `get_submodule` name (e.g. `backbone.encoder.layers.3`, `...fc1`); here such a hook would never fire, so it is
+            refused up front with the list of servable layers instead of failing later inside `extract_embeddings`."""
+            names = super().register_hooks_for_layers(target_layers)
+            ok = set(self.servable_layers())
+            bad = [n for n in names if n not in ok]
+            if bad:
+                self.deregister_all_hooks()
+                self._hook_layers = []
+                raise ValueError(
+                    f"avex_b200 BEATs cannot serve forward hooks on {bad}: the fused CUDA forward materialises only "
+                    f"{sorted(ok, key=lambda n: (len(n), n))} (the layers `_discover_embedding_layers` reports; "
+                    "select them by name, index, 'all' or 'last_layer')."
+                )
+            return names
+
         def process_audio(self, x: torch.Tensor) -> torch.Tensor:
             audio = super().process_audio(x)
             if self.use_naturelm:

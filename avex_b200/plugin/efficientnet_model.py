@@ -69,6 +69,22 @@ def make_model_class(base):
                     if n == "model.features.0.0" or (n.endswith(".block.3.0") and "model.features." in n) or n == "model.features.8.0"
                 ]  # fmt: skip
 
+        def register_hooks_for_layers(self, target_layers) -> List[str]:
+            """base_model.py:101-200, restricted to the conv outputs the NHWC kernels materialise (the 17 layers
+            `_discover_embedding_layers` reports); any other module name is refused up front."""
+            names = super().register_hooks_for_layers(target_layers)
+            self._discover_embedding_layers()
+            ok = set(self._layer_names)
+            bad = [n for n in names if n not in ok]
+            if bad:
+                self.deregister_all_hooks()
+                self._hook_layers = []
+                raise ValueError(
+                    f"avex_b200 EfficientNet cannot serve forward hooks on {bad}: the fused CUDA forward materialises only "
+                    f"{self._layer_names} (select them by name, index, 'all' or 'last_layer')."
+                )
+            return names
+
         def _mel(self, x: torch.Tensor, normalize: bool):
             if x is None:
                 raise ValueError("Input tensor cannot be None")

@@ -32,6 +32,9 @@ extern "C" {
 
 const char* avexk_last_error(void);
 int avexk_version(void);
+/* sha256 prefix (32 hex digits) of the sources this binary was compiled from (csrc/*.cu, csrc/*.cuh, this header);
+ * avex_b200/_lib.py refuses to bind a library whose id differs from the sources next to it. */
+const char* avexk_build_id(void);
 /* number of kernel launches this library has enqueued since load (bench.py's `gpu_launches`). */
 long long avexk_launch_count(void);
 

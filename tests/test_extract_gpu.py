@@ -38,7 +38,7 @@ def _batches(n_batches, bs, T, with_mask):
 
 @pytest.mark.parametrize("aggregation,with_mask", [("mean", False), ("none", False), ("mean", True)])
 def test_extraction_loop_matches_direct_calls(tmp_path, aggregation, with_mask):
-    from avex_b200.extract import extract_embeddings_for_split, save_embeddings_arrays
+    from avex_b200.extract import extract_embeddings_for_split, load_embeddings_arrays, save_embeddings_arrays
 
     model = _model()
     batches = _batches(5, 3, 16000, with_mask)
@@ -64,13 +64,18 @@ def test_extraction_loop_matches_direct_calls(tmp_path, aggregation, with_mask):
         for li, n in enumerate(names):
             want = torch.cat([r[li].cpu() for r in ref])
             assert torch.equal(emb[n], want) and emb[n].shape[1:] == (48, 768)
-    path = save_embeddings_arrays(emb, labels, str(tmp_path / "split"), aggregation=aggregation)
+    path = save_embeddings_arrays(emb, labels, str(tmp_path / "split"), num_labels=15, aggregation=aggregation)
     assert os.path.exists(path)
     if path.endswith(".npz"):
         z = np.load(path)
         attrs = json.loads(bytes(z["__attrs__"]).decode())
-        assert attrs["extraction_complete"] and attrs["layer_names"] == list(emb.keys())
-        assert z["labels"].shape == (15,) and all(z[f"embeddings_{n}"].dtype == np.float32 for n in emb)
+        assert attrs["extraction_complete"] and attrs["layer_names"] == list(emb.keys()) and attrs["multi_layer"] is True
+        assert attrs["embedding_dims"] == [str(tuple(emb[n].shape[1:])) for n in emb] and attrs["num_labels"] == 15
+        assert attrs["stored_embedding_rank"] == [emb[n].dim() - 1 for n in emb]
+        assert z["labels"].shape == (15,) and z["labels"].dtype == np.int64
+        assert all(z[f"embeddings_{n}"].dtype == np.float32 for n in emb)
+    back, lab, nl = load_embeddings_arrays(path)
+    assert nl == 15 and torch.equal(lab, labels) and all(torch.equal(back[n], emb[n]) for n in emb)
 
 
 def test_extraction_loop_errors():
