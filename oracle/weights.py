@@ -84,6 +84,16 @@ def make_beats_weights(dims: BeatsDims = BeatsDims(), seed: int = 1, init: str =
     return W
 
 
+def make_predictor_weights(seed: int = 9, embed: int = 768, classes: int = 527) -> dict:
+    """`backbone.predictor` (beats.py:262-264, the AudioSet-527 head of fine-tuned checkpoints): seeded N(0, 0.05) weight and
+    N(0, 0.02) bias so that every logit is observable."""
+    rs = np.random.RandomState(seed)
+    return {
+        "backbone.predictor.weight": (rs.standard_normal((classes, embed)) * 0.05).astype(np.float32),
+        "backbone.predictor.bias": (rs.standard_normal((classes,)) * 0.02).astype(np.float32),
+    }
+
+
 def make_effnet_weights(seed: int = 3, num_classes: int = 0, bn_stats: dict | None = None) -> dict:
     """Deterministic synthetic EfficientNet-B0 weights with torchvision's state_dict keys (prefix `model.`, as
     avex/models/efficientnet.py:61-66 holds the network).  Conv weights: fan-out normal (torchvision's init,

@@ -58,3 +58,17 @@ def beats_cases() -> dict:
         # tolerances (cos >= 0.999, max-abs <= 2e-2 in bf16) were calibrated on
         "L12_1x10s_refinit": dict(layers=12, wseed=5, init="reference", wav=_randn(1234, 1, 160000) * np.float32(0.1), keep_hooks=[0, 1, 12]),
     }
+
+
+def beats_long_case() -> dict:
+    """BASELINE.json configs[4] shape: ONE unmasked 60 s clip (N = 2992 tokens) through a 2-layer model -- exercises bias-vector
+    entries for |j - i| >= 496 (the log-bucket region and the max_distance = 800 saturation) through the product path.
+    Token axis sub-sampled by `stride` in the fixture to keep it small."""
+    return dict(layers=2, wseed=6, wav=_randn(31, 1, 960000) * np.float32(0.1), keep_hooks=[0, 2], stride=8)
+
+
+def predictor_case() -> dict:
+    """The AudioSet predictor branch (beats.py:369-380): logits = predictor(x), masked mean over tokens."""
+    c = dict(beats_cases()["L2_2x2s_mask"])
+    c["pseed"] = 9
+    return c

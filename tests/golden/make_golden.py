@@ -33,7 +33,7 @@ import torch  # noqa: E402
 from oracle import beats_encoder as OE  # noqa: E402
 from oracle import kaldi_fbank as OF  # noqa: E402
 from oracle import relpos as OR  # noqa: E402
-from oracle.weights import make_beats_weights  # noqa: E402
+from oracle.weights import make_beats_weights, make_predictor_weights  # noqa: E402
 
 torch.set_num_threads(os.cpu_count() or 1)
 REPORT: dict = {"reference": "earthspecies/avex v1.2.0 @ /root/reference", "torch": torch.__version__, "cases": {}}
@@ -187,8 +187,59 @@ def gen_beats():
         np.savez_compressed(os.path.join(HERE, f"beats_{cname}.npz"), **save)
 
 
+def gen_beats_long():
+    """One unmasked 60 s clip (config #5 shape) through the reference; token axis sub-sampled in the fixture."""
+    case = cases.beats_long_case()
+    dims = OE.BeatsDims(layers=case["layers"])
+    W = make_beats_weights(dims, seed=case["wseed"])
+    model = build_ref_beats(case["layers"], W)
+    x = torch.from_numpy(case["wav"])
+    st = case["stride"]
+    model.register_hooks_for_layers(["all"])
+    with torch.no_grad():
+        feats = model(x).numpy()
+    hooks = [h.numpy() for h in model.extract_embeddings(x, aggregation="none")]
+    pooled_hooks = model.extract_embeddings(x, aggregation="mean").numpy()
+    assert feats.shape == (1, 2992, 768), feats.shape
+    save = {"final": feats[:, ::st].astype(np.float32), "final_pooled": feats.mean(axis=1).astype(np.float32),
+            "pooled_hooks_mean": pooled_hooks.astype(np.float32)}
+    for li in case["keep_hooks"]:
+        save[f"hook{li}"] = hooks[li][:, ::st].astype(np.float32)
+    orc = OE.beats_forward(W, case["wav"], None, dims)
+    entry = {"input_sha": sha(case["wav"]), "layers": case["layers"], "tokens": int(feats.shape[1]), "stride": st,
+             "final_oracle_vs_ref": diff(orc["x"], feats), "fc2_last_oracle_vs_ref": diff(orc["fc2"][-1], hooks[-1])}
+    REPORT["cases"]["beats/L2_1x60s"] = entry
+    print("beats long", entry)
+    np.savez_compressed(os.path.join(HERE, "beats_L2_1x60s.npz"), **save)
+
+
+def gen_predictor():
+    """`BEATs.extract_features(feature_only=False)` with the predictor head (beats.py:369-380), with and without a padding mask."""
+    case = cases.predictor_case()
+    dims = OE.BeatsDims(layers=case["layers"])
+    W = make_beats_weights(dims, seed=case["wseed"])
+    P = make_predictor_weights(case["pseed"])
+    model = build_ref_beats(case["layers"], {**W, **P})
+    assert model.backbone.predictor is not None
+    assert torch.equal(model.backbone.predictor.weight, torch.from_numpy(P["backbone.predictor.weight"]))
+    x, m = torch.from_numpy(case["wav"]), torch.from_numpy(case["mask"])
+    with torch.no_grad():
+        lg_mask, km = model.backbone.extract_features(x, m, feature_only=False)
+        lg_none, _ = model.backbone.extract_features(x, None, feature_only=False)
+    assert lg_mask.shape == (2, 527) and km.any()
+    orc = OE.beats_forward(W, case["wav"], case["mask"], dims)
+    lg = orc["x"] @ P["backbone.predictor.weight"].T + P["backbone.predictor.bias"]
+    lg[orc["key_pad"]] = 0
+    mine = lg.sum(1) / (~orc["key_pad"]).sum(1)[:, None]
+    entry = {"input_sha": sha(case["wav"]), "oracle_vs_ref_masked": diff(mine, lg_mask.numpy())}
+    REPORT["cases"]["beats/predictor"] = entry
+    print("predictor", entry)
+    np.savez_compressed(os.path.join(HERE, "beats_predictor.npz"), logits_mask=lg_mask.numpy().astype(np.float32),
+                        logits_nomask=lg_none.numpy().astype(np.float32))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["fbank", "relpos", "beats"]
+    which = sys.argv[1:] or ["fbank", "relpos", "beats", "beats_long", "predictor"]
     rp = os.path.join(HERE, "REPORT.json")
     if os.path.exists(rp):
         try:
@@ -201,6 +252,10 @@ if __name__ == "__main__":
         gen_relpos()
     if "beats" in which:
         gen_beats()
+    if "beats_long" in which:
+        gen_beats_long()
+    if "predictor" in which:
+        gen_predictor()
     with open(rp, "w") as f:
         json.dump(REPORT, f, indent=1, sort_keys=True)
     print("wrote", rp)

@@ -130,6 +130,72 @@ def test_batch_independence_and_full_size():
     _cmp("10s clip vs oracle", one.cpu().numpy(), orc["x"])
 
 
+def test_60s_unmasked_against_reference_golden():
+    """BASELINE config #5 shape against the REFERENCE (not the kernel itself): one unmasked 60 s clip, N = 2992, bias offsets
+    up to +-2991 -- the log-bucket region and the max_distance saturation go through `relative_bias_vector` and the kernel's
+    in-tile Toeplitz indexing.  The fixture keeps every 8th token."""
+    case = cases.beats_long_case()
+    g = np.load(os.path.join(G, "beats_L2_1x60s.npz"))
+    model, W = _build(case["layers"], case["wseed"])
+    wav = torch.from_numpy(case["wav"]).cuda()
+    st = case["stride"]
+    with torch.no_grad():
+        feats = model(wav)
+    assert feats.shape == (1, 2992, 768)
+    _cmp("60s/final", feats[:, ::st].cpu().numpy(), g["final"])
+    _cmp("60s/final_pooled", feats.mean(dim=1).cpu().numpy(), g["final_pooled"], atol=2e-3, cos_min=0.9999)
+    model.register_hooks_for_layers(["all"])
+    hooks = model.extract_embeddings(wav, aggregation="none")
+    for li in case["keep_hooks"]:
+        _cmp(f"60s/hook{li}", hooks[li][:, ::st].cpu().numpy(), g[f"hook{li}"])
+    pooled = model.extract_embeddings(wav, aggregation="mean")
+    _cmp("60s/pooled_hooks_mean", pooled.cpu().numpy(), g["pooled_hooks_mean"], atol=1e-2, cos_min=0.9999)
+    model.backbone.precision = "fp32"
+    with torch.no_grad():
+        f32 = model(wav)
+    _cmp("fp32 60s/final", f32[:, ::st].cpu().numpy(), g["final"], atol=1e-3, cos_min=0.99999)
+
+
+def test_predictor_logits_against_reference_golden():
+    """The AudioSet predictor branch of fine-tuned checkpoints (beats.py:369-380) with and without a padding mask."""
+    from oracle.weights import make_predictor_weights
+
+    case = cases.predictor_case()
+    g = np.load(os.path.join(G, "beats_predictor.npz"))
+    model, W = _build(case["layers"], case["wseed"])
+    P = make_predictor_weights(case["pseed"])
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in P.items()}, strict=False)
+    assert not unexpected and model.backbone.predictor is not None
+    wav, mask = torch.from_numpy(case["wav"]).cuda(), torch.from_numpy(case["mask"]).cuda()
+    with torch.no_grad():
+        lg_m, km = model.backbone.extract_features(wav, mask, feature_only=False)
+        lg_n, _ = model.backbone.extract_features(wav, None, feature_only=False)
+    assert km is not None and km.any() and lg_m.shape == (2, 527)
+    _cmp("predictor logits (mask)", lg_m.cpu().numpy(), g["logits_mask"], atol=1e-2, cos_min=0.9999)
+    _cmp("predictor logits (no mask)", lg_n.cpu().numpy(), g["logits_nomask"], atol=1e-2, cos_min=0.9999)
+
+
+def test_bench_shape_256x10s():
+    """The bench configuration itself (256 x 10 s, M = 126 976 token rows, 496 CTA-pair tiles per GEMM): every clip of the big
+    batch must equal the same clip run alone (bit-identical: tiles never mix clips' rows in any reduction), and the fused
+    mean-pool must equal the mean of the features."""
+    model, W = _build(12, 3)
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    wav = torch.randn(256, 160000, device="cuda", generator=g) * 0.1
+    with torch.no_grad():
+        res = model.backbone.run(wav, None, want_features=True, want_pooled=True)
+        full, pooled = res["features"], res["pooled"]
+        assert full.shape == (256, 496, 768) and torch.isfinite(full).all()
+        for i in (0, 100, 255):
+            one = model(wav[i : i + 1])
+            assert torch.equal(full[i], one[0]), i
+        sub = model(wav[128:192])
+        assert torch.equal(full[128:192], sub)
+    assert torch.allclose(pooled, full.mean(dim=1), atol=2e-5, rtol=1e-5)
+    orc = OE.beats_forward(W, wav[255:256].cpu().numpy(), None, OE.BeatsDims(layers=12))
+    _cmp("clip 255 of 256 vs oracle", full[255:256].cpu().numpy(), orc["x"])
+
+
 def test_long_clip_equals_short_clip_under_padding_mask():
     """BASELINE config #5 shape (60 s clips, N = 2992 tokens), checked through a size-independent property instead of a
     60 s oracle run: a 10 s clip followed by 50 s of padding (samples >= 992 frames * 160 masked, so tokens >= 496 are

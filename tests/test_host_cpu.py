@@ -50,3 +50,74 @@ def test_no_cpu_fallback():
     fb = KaldiFbank()
     with pytest.raises(_lib.AvexkError):
         fb(torch.zeros(1, 16000))
+
+
+@pytest.mark.parametrize("n_tokens", [248, 496, 2992])
+def test_product_relpos_bucket_and_bias_vector_against_reference_golden(n_tokens):
+    """`avex_b200.beats.relative_position_bucket` / `relative_bias_vector` are what the CUDA attention consumes; hold THEM (not
+    only the oracle's copy) to the reference's `_relative_positions_bucket` output over offsets -3100..3100 (backbone.py:438-473),
+    including the log-bucket region (|d| >= 80) and the saturation at max_distance = 800 that only 60 s clips reach."""
+    from avex_b200.beats import relative_bias_vector, relative_position_bucket
+
+    g = np.load(os.path.join(G, "relpos_buckets.npz"))
+    rel, want = torch.from_numpy(g["rel"].astype(np.int64)), g["bucket"].astype(np.int64)
+    got = relative_position_bucket(rel, 320, 800).numpy()
+    assert np.array_equal(got, want)
+    assert got[rel.numpy() == 800].tolist() == [319] and got[rel.numpy() == -3100].tolist() == [159]
+    table = torch.arange(320 * 12, dtype=torch.float32).reshape(320, 12)
+    vec = relative_bias_vector(table, n_tokens, 320, 800).numpy()
+    assert vec.shape == (12, 2 * n_tokens - 1)
+    lo = 3100 - (n_tokens - 1)
+    idx = want[lo : lo + 2 * n_tokens - 1]  # offsets -(N-1) .. N-1
+    assert np.array_equal(vec, table.numpy()[idx].T)
+    # Toeplitz property the kernel relies on: bias[h, i, j] = vec[h, j - i + N - 1] equals the reference's [N, N] gather
+    i, j = 3, n_tokens - 2
+    assert vec[5, j - i + n_tokens - 1] == table[want[3100 + (j - i)], 5]
+
+
+def test_loader_refuses_stale_binary(tmp_path, monkeypatch):
+    """The .so is git-ignored and ships with the snapshot: `_lib.load()` must notice a binary built from other sources."""
+    from avex_b200 import build
+
+    assert build.binary_id() == build.source_id() == _lib.load().avexk_build_id().decode()
+    monkeypatch.setattr(build, "source_id", lambda: "0" * 32)
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.AvexkError, match="stale"):
+        _lib.load()
+
+
+def test_hook_selectors_outside_the_fused_path_are_refused():
+    """names the reference would accept but the fused forward never materialises must fail at registration."""
+    from avex_b200 import plugin
+    from avex_b200.plugin import beats_model  # noqa: F401
+
+    plugin.register_model("cpu_hook_test", plugin.ModelSpec(name="beats", device="cpu", init_config=dict(encoder_layers=2)))
+    model = plugin.load_model("cpu_hook_test", device="cpu", return_features_only=True)
+    assert model.register_hooks_for_layers([0, -1]) == ["backbone.post_extract_proj", "backbone.encoder.layers.1.fc2"]
+    for bad in ("backbone.encoder.layers.1", "backbone.encoder.layers.0.fc1", "backbone.encoder.layer_norm"):
+        with pytest.raises(ValueError, match="cannot serve forward hooks"):
+            model.register_hooks_for_layers([bad])
+        assert not model._hooks and not model._hook_layers
+    with pytest.raises(ValueError, match="not found"):
+        model.register_hooks_for_layers(["backbone.nope"])
+
+
+def test_model_copies_and_pickles_without_native_handles():
+    import copy
+    import pickle
+
+    from avex_b200.beats import BEATs, BEATsConfig
+
+    m = BEATs(BEATsConfig(encoder_layers=1))
+    m._engine, m._engine_key = ctypes.c_void_p(1234), ("x",)  # what a forward leaves behind
+    m.fbank._handle = ctypes.c_void_p(99)
+    c = copy.deepcopy(m)
+    assert c._engine is None and c.fbank._handle is None
+    assert torch.equal(c.post_extract_proj.weight, m.post_extract_proj.weight)
+    assert c.encoder.layers[0].self_attn.relative_attention_bias is c.encoder.layers[0].self_attn.relative_attention_bias
+    # whole-module pickling is refused by torch itself for the weight-norm parametrised pos-conv (the reference has the same
+    # limit); the pieces that hold native handles must not be what blocks it
+    f = pickle.loads(pickle.dumps(m.fbank))
+    assert f._handle is None and torch.equal(f.window, m.fbank.window)
+    assert m.__getstate__()["_engine"] is None
+    m._engine, m.fbank._handle = None, None  # nothing real to destroy

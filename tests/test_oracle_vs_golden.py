@@ -116,6 +116,43 @@ def test_beats_encoder(cname):
         assert (out["key_pad"] == g["key_pad"]).all()
 
 
+def test_beats_encoder_60s_unmasked():
+    """Config #5 shape: one unmasked 60 s clip (N = 2992), bias offsets up to +-2991 (saturated buckets)."""
+    case = cases.beats_long_case()
+    g = np.load(os.path.join(G, "beats_L2_1x60s.npz"))
+    assert _sha(case["wav"]) == REPORT["beats/L2_1x60s"]["input_sha"]
+    dims = OE.BeatsDims(layers=case["layers"])
+    W = make_beats_weights(dims, seed=case["wseed"])
+    out = OE.beats_forward(W, case["wav"], None, dims)
+    st = case["stride"]
+    assert out["x"].shape == (1, 2992, 768)
+    np.testing.assert_allclose(out["x"][:, ::st], g["final"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(out["x"].mean(axis=1), g["final_pooled"], atol=1e-4, rtol=1e-4)
+    hooks = [out["hook0"]] + out["fc2"]
+    for li in case["keep_hooks"]:
+        np.testing.assert_allclose(hooks[li][:, ::st], g[f"hook{li}"], atol=1e-4, rtol=1e-4)
+
+
+def test_predictor_branch():
+    """beats.py:369-380: logits = predictor(x); padded tokens zeroed, sum / valid count (mean without a mask)."""
+    from oracle.weights import make_predictor_weights
+
+    case = cases.predictor_case()
+    g = np.load(os.path.join(G, "beats_predictor.npz"))
+    dims = OE.BeatsDims(layers=case["layers"])
+    W = make_beats_weights(dims, seed=case["wseed"])
+    P = make_predictor_weights(case["pseed"])
+    for key, mask in (("logits_mask", case["mask"]), ("logits_nomask", None)):
+        out = OE.beats_forward(W, case["wav"], mask, dims)
+        lg = out["x"] @ P["backbone.predictor.weight"].T + P["backbone.predictor.bias"]
+        if mask is not None:
+            lg[out["key_pad"]] = 0
+            lg = lg.sum(1) / (~out["key_pad"]).sum(1)[:, None]
+        else:
+            lg = lg.mean(1)
+        np.testing.assert_allclose(lg, g[key], atol=1e-4, rtol=1e-4)
+
+
 @pytest.mark.parametrize("cname", ["L2_2x2s_mask", "L12_1x2s"])
 def test_torch_flavour_of_the_oracle(cname):
     """oracle/beats_torch.py (the timed CPU baseline) against the same reference goldens."""
