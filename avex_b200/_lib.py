@@ -66,6 +66,7 @@ SIGNATURES = {
     "avexk_fbank_destroy": (None, [_vp]),
     "avexk_fbank_num_frames": (_i, [_i]),
     "avexk_fbank_forward": (_i, [_vp, _vp, _i, _i, _ll, _f, _f, _f, _i, _i, _vp, _vp, _i, _vp]),
+    "avexk_fbank_patch_operand": (_i, [_vp, _vp, _i, _i, _ll, _f, _f, _f, _vp, _vp]),
     "avexk_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _ll, _i, _vp]),
     "avexk_beats_set_precision": (_i, [_vp, _i]),
     "avexk_gemm_ln_scratch_bytes": (_sz, [_i]),

@@ -86,7 +86,6 @@ size_t workspace_bytes(const avexk_beats_dims& d, int B, int T, int precision = 
   const long long C = d.embed, E = d.patch_embed, Ff = d.ffn, G = d.conv_groups;
   auto al = [](long long b) { return (size_t)((b + 255) & ~255LL); };
   size_t s = 0;
-  s += al((long long)B * F * 128 * 4);  // fbank
   s += al(M * 768 * 2);                 // patch operand [hi|lo|hi]
   s += al(M * E * 4);                   // patch-embed out
   s += al(M * E * 3 * 2);               // LN(512) bf16 [hi|lo|hi]
@@ -234,7 +233,7 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   AVEXK_CHECK_ARG(wav && fbank && bias_vec && workspace, "avexk_beats_forward: null argument");
   AVEXK_CHECK_ARG(out || pooled || hook_out, "avexk_beats_forward: no output requested");
   const avexk_beats_dims& d = h->d;
-  const int F = avexk_fbank_num_frames(T), N = avexk_beats_num_tokens(T);
+  const int N = avexk_beats_num_tokens(T);
   AVEXK_CHECK_ARG(B > 0 && N > 0, "avexk_beats_forward: clip too short (B=%d T=%d -> %d tokens)", B, T, N);
   const long long M = (long long)B * N;
   AVEXK_CHECK_ARG(M < (1LL << 31), "avexk_beats_forward: too many token rows (%lld)", M);
@@ -244,7 +243,6 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   const float alpha = powf(2.0f * (float)d.layers, 0.25f);  // backbone.py:306
 
   Carver cw{reinterpret_cast<char*>(workspace), workspace_bytes};
-  float* fb = cw.take<float>((size_t)B * F * 128);
   __nv_bfloat16* pa = cw.take<__nv_bfloat16>((size_t)M * 768);
   float* pe = cw.take<float>((size_t)M * E);
   __nv_bfloat16* peb = cw.take<__nv_bfloat16>((size_t)M * E * 3);
@@ -287,8 +285,8 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   };
 
   // ---- front end: fbank -> patch embed -> LN -> post_extract_proj (beats.py:344-359) -----------------------------
-  TRY(avexk_fbank_forward(fbank, wav, B, T, wav_stride, 32768.0f, d.fbank_mean, 1.0f / (2.0f * d.fbank_std), 0, 0, nullptr, fb, 0, stream));
-  TRY(launch_patchify(fb, B, F, pa, st));
+  // the fbank kernel writes the [hi|lo|hi] operand of the patch-embedding GEMM directly: no [B,F,128] tensor, no im2col pass
+  TRY(avexk_fbank_patch_operand(fbank, wav, B, T, wav_stride, 32768.0f, d.fbank_mean, 1.0f / (2.0f * d.fbank_std), pa, stream));
   TRY(gemm(pa, 768, h->patch_w, E, nullptr, 0, nullptr, nullptr, 0.f, pe, 0));
   TRY(launch_layernorm(pe, (int)M, E, h->ln0_w, h->ln0_b, d.ln_eps, nullptr, peb, st, 1));
   TRY(gemm(peb, 3 * E, h->proj_w, C, h->proj_b, 0, nullptr, nullptr, 0.f, x0, 0));

@@ -1,6 +1,7 @@
-// elementwise.cu -- the memory-bound glue of the BEATs path: LayerNorm, patchify (im2col of the 16x16 patch
-// embedding), pos-conv operand packing, masked mean-pool, weight packing.  All HBM-bound: one pass, 16-byte
+// elementwise.cu -- the memory-bound glue of the BEATs path: LayerNorm, pos-conv operand packing, masked mean-pool, weight packing.  All HBM-bound: one pass, 16-byte
 // vector accesses, a warp per row with shuffle reductions.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -61,38 +62,18 @@ layernorm_kernel(const float* __restrict__ x, int M, const float* __restrict__ g
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// patchify: normalised fbank [B,F,128] fp32 -> A [B*N, 3*256] bf16 ([hi|lo|hi]), row = b*N + tp*8 + fp, col = i*16 + j,
-// value fb[b, tp*16+i, fp*16+j]  (Conv2d(1,512,16,16,stride 16) as im2col; beats.py:349-352).
-// One thread per (b, tp, i, fp): reads 16 consecutive floats, writes 16 consecutive bf16.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-patchify_kernel(const float* __restrict__ fb, int B, int F, int Tp, __nv_bfloat16* __restrict__ A) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * Tp * 16 * 8;
-  if (idx >= total) return;
-  const int fp = idx & 7, i = (idx >> 3) & 15;
-  const long long bt = idx >> 7;
-  const int tp = bt % Tp, b = bt / Tp;
-  const float4* src = reinterpret_cast<const float4*>(fb + ((size_t)b * F + tp * 16 + i) * 128 + fp * 16);
-  const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
-  // 3-term split-bf16 operand [hi | lo | hi], row pitch 768: the front end carries the widest dynamic range and
-  // dominates the end-to-end bf16 error (tools/emulate_bf16.py), while costing 0.5 % of the FLOPs.
-  const uint2 h0 = make_uint2(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w)), h1 = make_uint2(pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
-  const uint2 h2 = make_uint2(pack_bf16(v2.x, v2.y), pack_bf16(v2.z, v2.w)), h3 = make_uint2(pack_bf16(v3.x, v3.y), pack_bf16(v3.z, v3.w));
-  const uint2 l0 = split_lo4(v0, h0), l1 = split_lo4(v1, h1), l2 = split_lo4(v2, h2), l3 = split_lo4(v3, h3);
-  uint4* dst = reinterpret_cast<uint4*>(A + ((size_t)b * Tp * 8 + tp * 8 + fp) * 768 + i * 16);
-  dst[0] = make_uint4(h0.x, h0.y, h1.x, h1.y);
-  dst[1] = make_uint4(h2.x, h2.y, h3.x, h3.y);
-  dst[32] = make_uint4(l0.x, l0.y, l1.x, l1.y);  // + 256 elements
-  dst[33] = make_uint4(l2.x, l2.y, l3.x, l3.y);
-  dst[64] = make_uint4(h0.x, h0.y, h1.x, h1.y);  // + 512 elements
-  dst[65] = make_uint4(h2.x, h2.y, h3.x, h3.y);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// pos-conv operand: x0 [M, C] fp32 -> xg [M, G*64] bf16 (each group's C/G = 48 channels padded to 64 so that one
+// pos-conv operand: x0 [M, C] fp32 -> xg [M, G*64] fp16 (16-bit storage typed __nv_bfloat16 in the signatures) (each group's C/G = 48 channels padded to 64 so that one
 // tap of one group is a 128-byte TMA row).  Rows of padded tokens are zeroed (backbone.py:169-170) in xg AND in x0.
 // ---------------------------------------------------------------------------------------------------------
+// The pos-conv operands are FP16, not bf16: the projection output is bounded (LayerNorm(512) -> Linear), the tensor core runs
+// kind::f16 at the same rate for both formats, and the three extra mantissa bits matter -- the 6144-term pos-conv sum was the
+// largest single contributor to the end-to-end error of the bf16 path (tools/emulate_bf16.py: final max-abs 0.0196 -> 0.0039
+// on the perturbed-weights golden).  Values beyond the fp16 range saturate instead of becoming inf.
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
 __global__ void __launch_bounds__(256)
 group_pad_kernel(float* __restrict__ x0, const uint8_t* __restrict__ key_pad, long long M, int G, int cg,
                  __nv_bfloat16* __restrict__ xg) {
@@ -110,7 +91,7 @@ group_pad_kernel(float* __restrict__ x0, const uint8_t* __restrict__ key_pad, lo
       src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const float4 a = src[0], b = src[1];
-      o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+      o = make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
     }
   }
   reinterpret_cast<uint4*>(xg + (size_t)row * (G * 64) + g * 64)[ch] = o;
@@ -196,7 +177,8 @@ __global__ void posconv_pack_kernel(const float* __restrict__ v, const float* __
     const int co = q % cg, t = (q / cg) % K, grp = q / ((long long)cg * K);
     float w = 0.f;
     if (ci < cg) w = g[t] * v[((size_t)(grp * cg + co) * cg + ci) * K + t] / nrm[t];
-    W[i] = __float2bfloat16_rn(w);
+    const __half hw = __float2half_rn(w);  // weight-normalised taps, |w| << 1: fp16 keeps three more bits than bf16
+    W[i] = *reinterpret_cast<const __nv_bfloat16*>(&hw);
   }
 }
 
@@ -229,15 +211,6 @@ int launch_layernorm(const float* x, int M, int C, const float* gamma, const flo
     default: layernorm_kernel<8><<<grid, 256, 0, st>>>(x, M, gamma, beta, eps, out_f32, ob, split3); break;
   }
   prof_end(st);
-  AVEXK_LAUNCH_CHECK();
-  return AVEXK_OK;
-}
-
-int launch_patchify(const float* fb, int B, int F, __nv_bfloat16* A, cudaStream_t st) {
-  const int Tp = F / 16;
-  const long long total = (long long)B * Tp * 128;
-  if (total == 0) return AVEXK_OK;
-  patchify_kernel<<<ceil_div(total, 256), 256, 0, st>>>(fb, B, F, Tp, A);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
 }

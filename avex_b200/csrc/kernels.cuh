@@ -21,7 +21,6 @@ int conv1x1_launch(const void* A, const void* W, int M, int N, int K, const floa
 int launch_layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, float* out_f32,
                      void* out_bf16, cudaStream_t st, int split3 = 0);
 int launch_f32_to_bf16_split3(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t st);
-int launch_patchify(const float* fb, int B, int F, __nv_bfloat16* A, cudaStream_t st);
 int launch_group_pad(float* x0, const uint8_t* key_pad, long long M, int G, int cg, __nv_bfloat16* xg, cudaStream_t st);
 int launch_mean_pool(const float* x, const uint8_t* key_pad, int any_pad, int B, int N, int C, float* out, cudaStream_t st);
 int launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);

@@ -156,7 +156,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM, NCOL);
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * BM, NCOL);  // fp16 operands: see elementwise.cu group_pad_kernel
       int stage = 0, it = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += num_units, ++it) {

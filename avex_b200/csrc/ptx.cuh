@@ -279,6 +279,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// fp16 x fp16 -> fp32 (a_format = b_format = 0), both operands K-major: same rate as bf16, three more mantissa bits --
+// used where the operand range is bounded (pos-conv)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 
 }  // namespace ptx
 }  // namespace avexk

@@ -155,6 +155,25 @@ class KaldiFbank(nn.Module):
         _lib.check(rc, "avexk_fbank_forward")
         return out
 
+    def patch_operand(self, waveforms: torch.Tensor, *, prescale: float = 1.0, norm_mean: float = 0.0, norm_std2: float = 1.0) -> torch.Tensor:
+        """The normalised fbank as the bf16 [hi|lo|hi] operand of the 16x16 patch-embedding GEMM, [B * N, 768] with
+        N = 8 * (frames // 16), written directly by the fbank kernel (what `avexk_beats_forward` uses internally)."""
+        if waveforms.dim() != 2 or not waveforms.is_cuda:
+            raise _lib.AvexkError("patch_operand expects [B, T] CUDA waveforms (no CPU fallback)")
+        x = waveforms if waveforms.dtype == torch.float32 else waveforms.float()
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        B, T = x.shape
+        n_tok = 8 * (self.num_frames(T) // 16)
+        out = torch.empty((B * n_tok, 768), device=x.device, dtype=torch.bfloat16)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().avexk_fbank_patch_operand(
+                self.handle(x.device), x.data_ptr(), B, T, x.stride(0) if B > 1 else max(T, x.stride(0)), float(prescale),
+                float(norm_mean), float(1.0 / norm_std2), out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream,
+            )  # fmt: skip
+        _lib.check(rc, "avexk_fbank_patch_operand")
+        return out
+
     def forward(self, waveforms: torch.Tensor) -> torch.Tensor:
         """`_BatchedFbank.forward` (beats.py:120-163): waveforms already scaled by 2**15 -> raw log-mel."""
         return self.run(waveforms)

@@ -73,6 +73,14 @@ int avexk_fbank_forward(const avexk_fbank_t* h, const float* wav, int B, int T, 
                         float norm_mean, float norm_scale, int out_frames, int per_utt, double* stats_ws, void* out,
                         int out_bf16, void* stream);
 
+/* The same front end writing the operand of the 16x16 patch-embedding GEMM directly (beats.py:349-352: Conv2d(1, 512, 16, stride 16)
+ * as im2col), so that the [B, F, 128] fbank never touches HBM:
+ *   out [B * N, 768] bf16, N = 8 * (frames / 16);  row = b * N + tp * 8 + fp,  col = i * 16 + j  <->  fbank[b, tp*16 + i, fp*16 + j]
+ *   columns [0,256) = bf16(v), [256,512) = bf16(v - bf16(v)), [512,768) = bf16(v) again (the [hi|lo|hi] half of the 3-term split
+ *   product with [hi|hi|lo] weights).  Bit-identical to splitting the fp32 output of avexk_fbank_forward. */
+int avexk_fbank_patch_operand(const avexk_fbank_t* h, const float* wav, int B, int T, long long wav_stride, float prescale,
+                              float norm_mean, float norm_scale, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Building blocks (each unit-testable against the oracle)
  * ---------------------------------------------------------------------------------------------------------- */

@@ -143,7 +143,7 @@ def test_60s_unmasked_against_reference_golden():
         feats = model(wav)
     assert feats.shape == (1, 2992, 768)
     _cmp("60s/final", feats[:, ::st].cpu().numpy(), g["final"])
-    _cmp("60s/final_pooled", feats.mean(dim=1).cpu().numpy(), g["final_pooled"], atol=2e-3, cos_min=0.9999)
+    _cmp("60s/final_pooled", feats.mean(dim=1).cpu().numpy(), g["final_pooled"], atol=5e-3, cos_min=0.9999)
     model.register_hooks_for_layers(["all"])
     hooks = model.extract_embeddings(wav, aggregation="none")
     for li in case["keep_hooks"]:

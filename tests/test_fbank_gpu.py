@@ -123,3 +123,27 @@ def test_full_size_properties(fbank):
     orc = OF.beats_preprocess(x[3:4, :32000].cpu().numpy())
     got = full[3, : orc.shape[1]].cpu().numpy()
     assert _stats(got, orc[0])[1] <= 1e-5
+
+
+@pytest.mark.parametrize("B,T", [(3, 16000), (2, 80000), (1, 160000), (2, 16 * 160 + 400 - 1), (5, 4000)])
+def test_patch_operand_equals_split_of_fp32_fbank(B, T):
+    """`avexk_fbank_patch_operand` (what the BEATs forward consumes) must be bit-identical to im2col + [hi|lo|hi] bf16 split of the
+    fp32 fbank the same kernel writes in its plain mode: row = b*N + tp*8 + fp, col = i*16 + j <-> fbank[b, tp*16+i, fp*16+j]."""
+    from avex_b200.fbank import KaldiFbank
+
+    fb = KaldiFbank().cuda()
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
+    wav = torch.randn(B, T, device="cuda", generator=g) * 0.1
+    kw = dict(prescale=32768.0, norm_mean=15.41663, norm_std2=2 * 6.55582)
+    full = fb.run(wav, **kw)
+    F = full.shape[1]
+    tp = F // 16
+    got = fb.patch_operand(wav, **kw)
+    assert got.shape == (B * tp * 8, 768)
+    if tp == 0:
+        return
+    patches = full[:, : tp * 16].reshape(B, tp, 16, 8, 16).permute(0, 1, 3, 2, 4).reshape(B * tp * 8, 256)
+    hi = patches.to(torch.bfloat16)
+    lo = (patches - hi.float()).to(torch.bfloat16)
+    want = torch.cat([hi, lo, hi], dim=1)
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
