@@ -71,6 +71,7 @@ SIGNATURES = {
     "avexk_beats_set_precision": (_i, [_vp, _i]),
     "avexk_gemm_ln_scratch_bytes": (_sz, [_i]),
     "avexk_gemm_bf16_ln": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
+    "avexk_gemm_bf16_ln_pooled": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _vp, _vp, _vp, _sz, _i, _vp, _vp, _vp, _vp]),
     "avexk_gemm_config": (_i, [_i]),
     "avexk_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "avexk_attention_gated": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -81,7 +82,7 @@ SIGNATURES = {
     "avexk_beats_load_weights": (_i, [_vp, C.POINTER(BeatsWeights), _vp]),
     "avexk_beats_num_tokens": (_i, [_i]),
     "avexk_beats_workspace_bytes": (_sz, [_vp, _i, _i]),
-    "avexk_beats_forward": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.POINTER(_vp), _vp, _vp, _sz, _vp]),
+    "avexk_beats_forward": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _sz, _vp]),
 }
 
 
@@ -117,7 +118,7 @@ SIGNATURES.update({
     "avexk_melspec_destroy": (None, [_vp]),
     "avexk_melspec_num_frames": (_i, [_i]),
     "avexk_melspec_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
-    "avexk_conv1x1_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "avexk_conv1x1_f16": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     "avexk_dwconv_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "avexk_effnet_create": (_i, [C.POINTER(EffnetBlockCfg), _i, _i, _i, C.POINTER(_vp)]),
     "avexk_effnet_destroy": (None, [_vp]),

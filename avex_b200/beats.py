@@ -341,8 +341,12 @@ class BEATs(nn.Module):
         want_features: bool = True,
         want_pooled: bool = False,
         hook_layers: Optional[list[int]] = None,
+        hook_pool: bool = False,
     ) -> dict:
-        """One fused forward.  Returns {"features", "pooled", "hooks": {idx: tensor [B,N,C]}, "padding_mask"}."""
+        """One fused forward.  Returns {"features", "pooled", "hooks": {idx: tensor}, "padding_mask"}.
+
+        Hooked tensors are [B,N,C] -- or, with `hook_pool=True`, their mean over the N tokens, [B,C], formed inside the fc2
+        epilogue without ever materialising [B,N,C] (what `extract_embeddings(aggregation="mean")` reduces them to)."""
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise _lib.AvexkError(
                 "avex_b200 BEATs is forward-only: call under torch.no_grad() / freeze_backbone=True "
@@ -378,15 +382,16 @@ class BEATs(nn.Module):
         pooled = torch.empty((B, Cdim), device=device, dtype=torch.float32) if want_pooled else None
         hooks: dict[int, torch.Tensor] = {}
         hook_ptrs = (C.c_void_p * (cfg.encoder_layers + 1))()
+        pool_ptrs = (C.c_void_p * (cfg.encoder_layers + 1))()
         for li in hook_layers or []:
-            hooks[li] = torch.empty((B, N, Cdim), device=device, dtype=torch.float32)
-            hook_ptrs[li] = hooks[li].data_ptr()
+            hooks[li] = torch.empty((B, Cdim) if hook_pool else (B, N, Cdim), device=device, dtype=torch.float32)
+            (pool_ptrs if hook_pool else hook_ptrs)[li] = hooks[li].data_ptr()
         bias_vec = self._bias_vec(N, device)
         with torch.cuda.device(device):
             rc = lib.avexk_beats_forward(
                 engine, x.data_ptr(), B, T, x.stride(0) if B > 1 else max(T, x.stride(0)), self.fbank.handle(device),
                 key_pad.data_ptr() if key_pad is not None else None, bias_vec.data_ptr(),
-                feats.data_ptr() if feats is not None else None, hook_ptrs,
+                feats.data_ptr() if feats is not None else None, hook_ptrs, pool_ptrs,
                 pooled.data_ptr() if pooled is not None else None,
                 self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream(device).cuda_stream,
             )  # fmt: skip
@@ -397,8 +402,15 @@ class BEATs(nn.Module):
         """Run the forward hooks registered on post_extract_proj / fc2 with the tensors the kernels produced."""
         for li, t in hooks.items():
             mod = self.post_extract_proj if li == 0 else self.encoder.layers[li - 1].fc2
-            out = t if li == 0 else t.transpose(0, 1)  # blocks run (T,B,C) in the reference, backbone.py:182
+            out = t if (li == 0 or t.dim() == 2) else t.transpose(0, 1)  # blocks run (T,B,C) in the reference, backbone.py:182
             out = call_forward_hooks(mod, out)
+
+    def hooks_are_only(self, handles) -> bool:
+        """True when every forward hook on the servable modules is one of `handles` (the ModelBase capture hooks): only then may
+        `extract_embeddings(aggregation="mean")` hand the hooks token-pooled [B,C] tensors instead of [B,N,C]."""
+        own = {h.id for h in handles}
+        mods = [self.post_extract_proj] + [blk.fc2 for blk in self.encoder.layers]
+        return all(hid in own for m in mods for hid in m._forward_hooks)
 
     def _hooked_layers(self) -> list[int]:
         idx = []

@@ -21,14 +21,17 @@
 //   warp 17      MMA issuer: S_g = Q_g K^T (128x128x64, K-major operands from shared memory), the gate logits Q_g Wg^T, and
 //                O_g += P_g V (128x64x128; A = P from TMEM, B = V consumed MN-major exactly as it lies in the qkv buffer --
 //                no transposed copy), tcgen05.commit -> mbarriers.  PV_g(t) is issued before S_g(t+1), which overwrites P.
-//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each; P_g as bf16 pairs over columns 0..31 and 64..95 of S_g),
-//                O_A @256, O_B @320 (fp32 128x64 each), gate logits @384 / @400.
+//   TMEM (512 columns): S_A @0, S_B @128 (fp32 128x128 each), O_A @256, O_B @320 (fp32 128x64 each), P_A @384, P_B @448
+//                (bf16 pairs, 64 columns each).  P has columns of its own -- the per-row gate arrives precomputed (QKV epilogue),
+//                which freed the columns its logits used to take -- so S_g(t+1) is issued BEFORE O_g += P_g(t) V(t) and the
+//                softmax warps wait for one MMA batch per tile instead of two.
 //   Shared memory: Q (2 tiles), a 5-stage K/V ring, the bias / mask tables -- the measured limiter before P moved to TMEM
 //                was the shared-memory pipe (64 % busy: bias-window loads 31 %, P stores 11 %, MMA operand reads 21 %).
 // Roofline: MUFU (one ex2 per score: B*H*N^2 per layer) and FP32 issue, not the tensor pipe; see DESIGN.md section 4.
 #include <math.h>
 
 #include "common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -53,23 +56,19 @@ constexpr int WIN_FLOATS = 1056;
 constexpr int OFF_Q = 0;                                 // [2] tiles
 constexpr int OFF_KV = OFF_Q + 2 * TILE_BYTES;           // [KV_STAGES] x (K tile, V tile)
 constexpr int OFF_OSTG = OFF_KV + KV_STAGES * 2 * TILE_BYTES;  // [16 softmax warps] x (32 rows x 64 bytes, 64-byte swizzle): O on its way out (TMA store)
-constexpr int OFF_WG = OFF_OSTG + 16 * 2048;  // gate weights as a 16 x 64 bf16 UMMA operand (K-major, 128-byte swizzle)
-constexpr int OFF_TAB = OFF_WG + 2048;
+constexpr int OFF_TAB = OFF_OSTG + 16 * 2048;
 constexpr int TAB_WIN = 0;                               // [2][WIN_FLOATS] float
 constexpr int TAB_MASK = TAB_WIN + 2 * WIN_FLOATS * 4;  // [2][128] float
 constexpr int TAB_PMAX = TAB_MASK + 2 * 128 * 4;         // exchange buffers: [2 parity][2][128] tile max, [2][128] row sums l, [128] shared estimate
 constexpr int TAB_BYTES = TAB_PMAX + 1024 * 4 + 16;  // + one int: first tile with a valid key
-constexpr int OFF_GATEB = OFF_TAB + 2 * TAB_BYTES;  // [2] float: gate bias
-constexpr int OFF_BAR = OFF_GATEB + 16;
+constexpr int OFF_BAR = OFF_TAB + 2 * TAB_BYTES;
 constexpr int SMEM_BYTES = 1024 + OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "attention_tc: shared memory budget");
 
 struct AttnTcArgs {
   int B, N, H;
   int n_items;             // B * H * ceil(N / 256): read from the constant bank where needed (a register-resident copy spilled)
-  const float* gate_w;     // [2,64]
-  const float* gate_b;     // [2]
-  const float* grep_a;     // [H]
+  const float* gate;       // [B*N, H]: gate_a * (gate_b * grep_a - 1) + 2 of every (token, head) (backbone.py:544-550)
   const float* bias_vec;   // [H, 2N-1]
   const uint8_t* key_pad;  // [B,N] or null
   __nv_bfloat16* out;      // [B*N, H*64]
@@ -130,20 +129,43 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __device__ __forceinline__ int win_copy_offset(int s) { return s == 0 ? 0 : (s == 1 ? 260 : (s == 2 ? 524 : 788)); }
 
-// x = S * scale + gate * bias (+ mask): two scores per packed fp32x2 instruction.  Software pipeline per 16-column
-// chunk: the TMEM load of chunk c+1 and the window loads of chunk c+1 are in flight while chunk c is processed
-// (tcgen05.wait::ld waits for every outstanding load, so the next load is issued right after the wait).
-#define AVEXK_SCORE_QUAD(R, lo, hi)                                                                                       \
-  float2 lo = __ffma2_rn(make_float2(__uint_as_float(R[4 * k + 0]), __uint_as_float(R[4 * k + 1])), s2,                    \
-                         __fmul2_rn(g2, make_float2(w[k].x, w[k].y)));                                                    \
-  float2 hi = __ffma2_rn(make_float2(__uint_as_float(R[4 * k + 2]), __uint_as_float(R[4 * k + 3])), s2,                    \
-                         __fmul2_rn(g2, make_float2(w[k].z, w[k].w)));                                                    \
-  if (chunk < 3) w[k] = lds128(win_addr + ((chunk + 1) * 16 + k * 4) * 4);                                               \
-  if (MASKED) {                                                                                                           \
-    const float4 mk = lds128(mask_addr + (chunk * 16 + k * 4) * 4);                                                       \
-    lo = __fadd2_rn(lo, make_float2(mk.x, mk.y));                                                                         \
-    hi = __fadd2_rn(hi, make_float2(mk.z, mk.w));                                                                         \
+// A tile is PLAIN (every key valid), RAGGED (the clip ends inside it: keys >= nv are dead -- every clip's last tile unless N is a
+// multiple of 128; handled by skipping dead 16-key chunks, no mask table) or MASKED (a padding mask kills keys inside it).
+enum { TILE_PLAIN = 0, TILE_MASKED = 1, TILE_RAGGED = 2 };
+
+// One 16-key chunk of a row: y = S * scale + (gate * bias - m_ref) (+ mask), two scores per packed fp32x2 instruction; tracks the
+// chunk max on y, p = 2^min(y, P_CLAMP) -> bf16 pairs, row-sum contribution.  BOUNDARY (ragged tiles only): the chunk straddles
+// the end of the clip, keys >= nv get -inf.  The window values of the NEXT chunk are fetched as the current ones are consumed.
+template <int KIND, bool BOUNDARY>
+__device__ __forceinline__ void score_chunk(const uint32_t (&R)[16], float4 (&w)[4], uint32_t next_win, bool fetch_next, uint32_t mask_chunk,
+                                            float2 g2, float2 s2, float2 nm2, int c0, int nv, float& mx, float2& sum2, uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 lo = __ffma2_rn(make_float2(__uint_as_float(R[4 * k + 0]), __uint_as_float(R[4 * k + 1])), s2,
+                           __ffma2_rn(g2, make_float2(w[k].x, w[k].y), nm2));
+    float2 hi = __ffma2_rn(make_float2(__uint_as_float(R[4 * k + 2]), __uint_as_float(R[4 * k + 3])), s2,
+                           __ffma2_rn(g2, make_float2(w[k].z, w[k].w), nm2));
+    if (fetch_next) w[k] = lds128(next_win + k * 16);
+    if (KIND == TILE_MASKED) {
+      const float4 mk = lds128(mask_chunk + k * 16);
+      lo = __fadd2_rn(lo, make_float2(mk.x, mk.y));
+      hi = __fadd2_rn(hi, make_float2(mk.z, mk.w));
+    }
+    if (BOUNDARY) {
+      lo.x = c0 + 4 * k + 0 < nv ? lo.x : -INFINITY;
+      lo.y = c0 + 4 * k + 1 < nv ? lo.y : -INFINITY;
+      hi.x = c0 + 4 * k + 2 < nv ? hi.x : -INFINITY;
+      hi.y = c0 + 4 * k + 3 < nv ? hi.y : -INFINITY;
+    }
+    mx = fmaxf(fmaxf(mx, fmaxf(lo.x, lo.y)), fmaxf(hi.x, hi.y));
+    // the reference max may lag the true max (it moves between tiles): clamp so bf16 P cannot overflow
+    const float2 p0 = make_float2(ex2(fminf(lo.x, P_CLAMP)), ex2(fminf(lo.y, P_CLAMP)));
+    const float2 p1 = make_float2(ex2(fminf(hi.x, P_CLAMP)), ex2(fminf(hi.y, P_CLAMP)));
+    sum2 = __fadd2_rn(sum2, __fadd2_rn(p0, p1));
+    pk[2 * k] = pack_bf16(p0.x, p0.y);
+    pk[2 * k + 1] = pack_bf16(p1.x, p1.y);
   }
+}
 
 // Reference estimate (only on the first tile with a valid key): the max of ONE 16-key chunk of the row, the chunk that holds
 // the clip's first valid key.  Both column halves of a row read the same chunk, so they agree without an exchange.  Any
@@ -173,13 +195,14 @@ __device__ __forceinline__ float score_est(uint32_t taddr, uint32_t win_addr, ui
   return mx;
 }
 
-// Stream the 64 scores once: p = 2^(min(x - m, P_CLAMP)) -> bf16 pairs -> back into TMEM, over the first half of the
-// thread's own score columns (chunk c of 16 fp32 scores becomes 8 packed columns at 8c: always columns this thread has
-// already read), where the PV MMA takes them as its A operand -- P never touches shared memory.  Accumulates the row sum
-// and tracks the tile max (used to move the reference max for the NEXT tile).  Nothing is kept in registers.
-template <bool MASKED>
-__device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale,
-                                            float m_ref, float& mx_out, float& sum_out) {
+// Stream the 64 scores once: p = 2^(min(x - m, P_CLAMP)) -> bf16 pairs -> into the group's P columns of TMEM (chunk c of 16
+// fp32 scores becomes 8 packed columns at 8c of the thread's half), where the PV MMA takes them as its A operand -- P never
+// touches shared memory.  Accumulates the row sum and tracks the tile max (used to move the reference max for the NEXT tile).
+// Nothing is kept in registers.
+template <int KIND>
+__device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t paddr, uint32_t pv_bar, uint32_t pv_parity, uint32_t sfree_bar,
+                                            int lane, uint32_t win_addr, uint32_t mask_addr, float gate, float qk_scale, float m_ref,
+                                            int col0, int nv, float& mx_out, float& sum_out) {
   float mx = -INFINITY;
   const float2 g2 = make_float2(gate, gate), s2 = make_float2(qk_scale, qk_scale), nm2 = make_float2(-m_ref, -m_ref);
   float2 sum2 = make_float2(0.f, 0.f);
@@ -191,35 +214,44 @@ __device__ __forceinline__ void stream_tile(uint32_t taddr, uint32_t win_addr, u
   ptx::tmem_ld_wait();
 #pragma unroll
   for (int chunk = 0; chunk < 4; ++chunk) {
+    const int c0 = col0 + chunk * 16;  // first key of this chunk inside the tile
     if (chunk < 3) tmem_ld_32x16(taddr + (chunk + 1) * 16, (chunk & 1) ? ra : rb);
     uint32_t pk[8];
+    const uint32_t nwin = win_addr + (chunk + 1) * 64, mchunk = mask_addr + chunk * 64;
+    const bool fetch = chunk < 3;
+    // warp-uniform three-way split on ragged tiles: chunk past the end of the clip (P = 0, no arithmetic), chunk straddling it
+    // (per-key predicate), chunk inside it (the plain code)
+    if (KIND == TILE_RAGGED && c0 >= nv) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float2 lo_, hi_;
-      if (chunk & 1) {
-        AVEXK_SCORE_QUAD(rb, lo, hi)
-        lo_ = lo; hi_ = hi;
-      } else {
-        AVEXK_SCORE_QUAD(ra, lo, hi)
-        lo_ = lo; hi_ = hi;
-      }
-      mx = fmaxf(fmaxf(mx, fmaxf(lo_.x, lo_.y)), fmaxf(hi_.x, hi_.y));
-      lo_ = __fadd2_rn(lo_, nm2);
-      hi_ = __fadd2_rn(hi_, nm2);
-      // the reference max may lag the true max (it moves between tiles): clamp so bf16 P cannot overflow
-      const float2 p0 = make_float2(ex2(fminf(lo_.x, P_CLAMP)), ex2(fminf(lo_.y, P_CLAMP)));
-      const float2 p1 = make_float2(ex2(fminf(hi_.x, P_CLAMP)), ex2(fminf(hi_.y, P_CLAMP)));
-      sum2 = __fadd2_rn(sum2, __fadd2_rn(p0, p1));
-      pk[2 * k] = pack_bf16(p0.x, p0.y);
-      pk[2 * k + 1] = pack_bf16(p1.x, p1.y);
+      for (int k = 0; k < 8; ++k) pk[k] = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (fetch) w[k] = lds128(nwin + k * 16);
+    } else if (KIND == TILE_RAGGED && c0 + 16 > nv) {
+      if (chunk & 1) score_chunk<KIND, true>(rb, w, nwin, fetch, mchunk, g2, s2, nm2, c0, nv, mx, sum2, pk);
+      else score_chunk<KIND, true>(ra, w, nwin, fetch, mchunk, g2, s2, nm2, c0, nv, mx, sum2, pk);
+    } else {
+      if (chunk & 1) score_chunk<KIND, false>(rb, w, nwin, fetch, mchunk, g2, s2, nm2, c0, nv, mx, sum2, pk);
+      else score_chunk<KIND, false>(ra, w, nwin, fetch, mchunk, g2, s2, nm2, c0, nv, mx, sum2, pk);
     }
-    if (chunk < 3) ptx::tmem_ld_wait();  // also orders the store below after the loads of the columns it overwrites
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + chunk * 8),
+    if (chunk < 3) ptx::tmem_ld_wait();
+    if (chunk == 2) {
+      // every score of S_g(t) is in registers (chunk 3 landed with the wait above): the issuer may overwrite S_g with S_g(t+1)
+      // while this warp still works on its last chunk -- a quarter of the tile's softmax time off the MMA round trip
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_a(sfree_bar);
+    }
+    if (chunk == 0) {  // P_g(t-1) must have been consumed by its PV before it is overwritten (long retired by now, as a rule)
+      ptx::mbar_wait_a(pv_bar, pv_parity);
+      ptx::tc_fence_after();
+    }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(paddr + chunk * 8),
                  "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                  : "memory");
   }
   tmem_st_wait();
-  mx_out = mx;
+  mx_out = mx + m_ref;  // back to the un-shifted domain: the caller compares tile maxima with the reference
   sum_out = sum2.x + sum2.y;
 }
 
@@ -252,9 +284,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   uint64_t* kv_empty = bars + 12;  // [KV_STAGES <= 8]
   uint64_t* s_full = bars + 20;    // [2]
   uint64_t* p_full = bars + 22;    // [2]
-  uint64_t* o_full = bars + 24;    // [2]
+  uint64_t* o_full = bars + 24;    // [2]  PV_g(t) retired (one phase per TILE): P_g may be rewritten, O_g is consistent
   uint64_t* o_free = bars + 26;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* s_free = bars + 30;    // [2]  S_g(t) has been read out of TMEM by all of the group's warps (one phase per tile)
   static_assert(KV_STAGES <= 8, "barrier layout");
 
   int tid;  // read once through a volatile asm: otherwise the compiler re-reads %tid.x (S2R, behind the MUFU queue) per item
@@ -265,18 +298,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   const int npairs = (N + 2 * BQ - 1) / (2 * BQ);
   const int n_items = a.n_items;
 
-  // Gate weights -> a 16-row UMMA B operand, once per CTA: rows 0,1 = bf16(w), rows 2,3 = bf16(w - hi) (the two halves
-  // are summed after the MMA, so the gate logits carry ~16 mantissa bits of w), rows 4..15 = 0.
-  for (int e = tid; e < 16 * HD; e += NTHREADS) {
-    const int row = e >> 6, col = e & 63;
-    const float w = row < 4 ? __ldg(a.gate_w + (row & 1) * HD + col) : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-    const __nv_bfloat16 v = row < 2 ? hi : __float2bfloat16_rn(w - __bfloat162float(hi));
-    const uint32_t off = row * 128 + (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2;
-    asm volatile("st.shared.b16 [%0], %1;" ::"r"(smem_a + OFF_WG + off), "h"(__bfloat16_as_ushort(v)) : "memory");
-  }
-  if (tid < 2) sts32(smem_a + OFF_GATEB + tid * 4, __ldg(a.gate_b + tid));
-  ptx::fence_proxy_async();  // the gate operand is read by the tensor core (async proxy)
   if (warp == WARP_MMA) {
     if (lane == 0) {
       ptx::prefetch_tensormap(&map_qkv);
@@ -288,6 +309,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         ptx::mbar_init(&p_full[g], GROUP_WARPS);
         ptx::mbar_init(&o_full[g], 1);
         ptx::mbar_init(&o_free[g], GROUP_WARPS);
+        ptx::mbar_init(&s_free[g], GROUP_WARPS);
       }
       for (int s = 0; s < KV_STAGES; ++s) {
         ptx::mbar_init(&kv_full[s], 1);
@@ -348,18 +370,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     if (lane == 0) {
       constexpr uint32_t idesc_s = ptx::make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = ptx::make_idesc_bf16(BQ, HD) | (1u << 16);  // B operand (V) is MN-major
-      constexpr uint32_t idesc_g = ptx::make_idesc_bf16(BQ, 16);
-      const uint32_t lo_wg = ptx::sw128_desc_lo(smem_a + OFF_WG);
       const uint32_t bar_a = smem_a + OFF_BAR;
-      constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_KVFULL = 32, B_KVEMPTY = 96, B_SFULL = 160, B_PFULL = 176, B_OFULL = 192, B_OFREE = 208;
+      constexpr uint32_t B_QFULL = 0, B_QEMPTY = 16, B_KVFULL = 32, B_KVEMPTY = 96, B_SFULL = 160, B_PFULL = 176, B_OFULL = 192, B_OFREE = 208,
+                         B_SFREE = 240;
       const uint32_t lo_q = ptx::sw128_desc_lo(smem_a + OFF_Q), lo_kv = ptx::sw128_desc_lo(smem_a + OFF_KV);
-      uint32_t gt0 = 0;   // global index (over this CTA's items) of the item's first K/V tile
-      uint32_t ipar = 0;  // bit g: parity of the items group g has processed
-      uint32_t tpar = 0;  // bit g: parity of the tiles group g has processed
-      auto issue_s = [&](int g, uint32_t gt) {
+      auto issue_s = [&](int g, uint32_t gt) {  // the caller has seen kv_full of the stage
         const uint32_t st = gt % KV_STAGES;
-        ptx::mbar_wait_a(bar_a + B_KVFULL + st * 8, (gt / KV_STAGES) & 1);  // returns at once if this phase was already observed
-        ptx::tc_fence_after();
         const uint32_t dq = lo_q + g * (TILE_BYTES >> 4), dk = lo_kv + st * (2 * TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
@@ -367,59 +383,72 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
                          k != 0 ? 1u : 0u);
         ptx::umma_commit_a(bar_a + B_SFULL + g * 8);
       };
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ng = (item % npairs) * 2 * BQ + BQ < N ? 2 : 1;  // Item::has_b
-        for (int g = 0; g < ng; ++g) {
-          ptx::mbar_wait_a(bar_a + B_QFULL + g * 8, (ipar >> g) & 1);
-          ptx::tc_fence_after();
-          // gate logits of the 128 query rows: G_g = Q_g Wg^T (128 x 16 x 64) -> TMEM columns 384 + 16 g; the commit of
-          // S_g(0) below covers them
+      // Two independent state machines, one per query-tile group, over this CTA's item list (ordinal k <-> item blockIdx.x + k *
+      // gridDim.x; K/V tile t of item k has the global index k * n_kv + t, which names its ring stage and barrier phase).  A group
+      // only waits for ITS OWN softmax warps: it starts the next item while the other group is still finishing the current one
+      // (the first version walked the items in lock step, which cost every group an MMA round trip plus the other group's
+      // remaining tile time at every item boundary).  The K/V ring couples them loosely: a stage is released by whichever
+      // group's PV on it comes last.
+      const int n_ord = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
+      auto has_group = [&](int g, int k) -> bool {  // group 1 only exists when the pair's second tile holds a valid query row
+        if (g == 0) return true;
+        const int item = blockIdx.x + k * gridDim.x;
+        return (item % npairs) * 2 * BQ + BQ < N;
+      };
+      // positions are packed (item ordinal << 8 | tile): one register each, and "is ahead of" is an integer compare
+      uint32_t ps[2] = {0, 0};  // next S_g
+      uint32_t pp[2] = {0, 0};  // next PV_g
+      const uint32_t pend = (uint32_t)n_ord << 8;
+      auto advance = [&](int g, uint32_t pos) -> uint32_t {  // next tile; past the item's last tile: first tile of g's next item
+        if ((int)(pos & 0xffu) + 1 < n_kv) return pos + 1;
+        uint32_t k = (pos >> 8) + 1;
+        while ((int)k < n_ord && !has_group(g, (int)k)) ++k;
+        return k << 8;
+      };
+      uint32_t qpar = 0, sfpar = 0, tpar = 0, opar = 0, sany = 0;  // bit g: parities of q_full / s_free / p_full / o_free; S ever issued
+      if (n_ord > 0 && !has_group(1, 0)) ps[1] = pp[1] = advance(1, (uint32_t)(n_kv - 1));
+      while (pp[0] < pend || pp[1] < pend) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            ptx::umma_bf16(tmem_base + 384 + g * 16, ptx::sw128_desc_from_lo(lo_q + g * (TILE_BYTES >> 4) + 2 * k),
-                           ptx::sw128_desc_from_lo(lo_wg + 2 * k), idesc_g, k != 0 ? 1u : 0u);
-          issue_s(g, gt0);
-          if (n_kv == 1) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);
-        }
-        uint32_t done = ng == 2 ? 0u : (uint32_t)n_kv << 16;  // tiles finished: group 0 in the low half, group 1 in the high half
-        while ((int)(done & 0xffffu) < n_kv || (int)(done >> 16) < n_kv) {
-#pragma unroll 1
-          for (int g = 0; g < 2; ++g) {
-            const int t = (done >> (16 * g)) & 0xffffu;
-            if (t >= n_kv) continue;
-            if (!ptx::mbar_try_wait_a(bar_a + B_PFULL + g * 8, (tpar >> g) & 1)) continue;  // P_g(t) stored, S_g(t) read out of TMEM
-            if (t + 1 < n_kv) {
-              // never block here: the stage of tile t+1 may only free up after the OTHER group's PV, issued by this thread
-              const uint32_t gn = gt0 + t + 1;
-              if (!ptx::mbar_try_wait_a(bar_a + B_KVFULL + (gn % KV_STAGES) * 8, (gn / KV_STAGES) & 1)) continue;
-            }
-            ptx::tc_fence_after();
-            if (t == 0) {
-              ptx::mbar_wait_a(bar_a + B_OFREE + g * 8, ((ipar >> g) & 1) ^ 1);  // previous item's O_g has been drained
+        for (int g = 0; g < 2; ++g) {
+          // ---- S_g(k, t): Q_g of the item landed (t = 0), the previous S of this group read out of TMEM, K(k, t) landed ----
+          if (ps[g] < pend) {
+            const uint32_t t = ps[g] & 0xffu, gt = (ps[g] >> 8) * n_kv + t;
+            bool ok = !((sany >> g) & 1) || ptx::mbar_try_wait_a(bar_a + B_SFREE + g * 8, (sfpar >> g) & 1);
+            if (ok && t == 0) ok = ptx::mbar_try_wait_a(bar_a + B_QFULL + g * 8, (qpar >> g) & 1);
+            if (ok) ok = ptx::mbar_try_wait_a(bar_a + B_KVFULL + (gt % KV_STAGES) * 8, (gt / KV_STAGES) & 1);
+            if (ok) {
               ptx::tc_fence_after();
+              issue_s(g, gt);
+              if ((sany >> g) & 1) sfpar ^= 1u << g;
+              sany |= 1u << g;
+              if (t == 0) qpar ^= 1u << g;
+              if ((int)t + 1 == n_kv) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);  // last S of the item: Q_g may be overwritten
+              ps[g] = advance(g, ps[g]);
             }
-            // O_g += P_g(t) V(t).  A: P as bf16 pairs in TMEM, inside the columns of S_g that its writer owned (keys
-            // 0..63 at columns 0..31, keys 64..127 at columns 64..95); B: V rows = keys (MN-major), 16 keys = 2048 bytes
-            const uint32_t st = (gt0 + t) % KV_STAGES;
+          }
+          // ---- O_g += P_g(k, t) V(k, t): P stored; first tile of an item: the previous item's O_g drained ----
+          if (pp[g] < pend && ptx::mbar_try_wait_a(bar_a + B_PFULL + g * 8, (tpar >> g) & 1)) {
+            ptx::tc_fence_after();
+            const uint32_t pos = pp[g], t = pos & 0xffu;
+            if (t == 0) {
+              ptx::mbar_wait_a(bar_a + B_OFREE + g * 8, ((opar >> g) & 1) ^ 1);
+              ptx::tc_fence_after();
+              opar ^= 1u << g;
+            }
+            // A: P as bf16 pairs in TMEM (keys 16 ks .. 16 ks + 15 at columns 8 ks of P_g); B: V rows = keys (MN-major), 16 keys = 2048 B
+            const uint32_t st = ((pos >> 8) * n_kv + t) % KV_STAGES;
             const uint32_t dv = lo_kv + st * (2 * TILE_BYTES >> 4) + (TILE_BYTES >> 4);
 #pragma unroll
-            for (int ks = 0; ks < BKV / 16; ++ks)
-              ptx::umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + g * 128 + (ks >> 2) * 64 + (ks & 3) * 8,
-                                ptx::sw128_desc_from_lo(dv + ks * (2048 >> 4)), idesc_o, (t | ks) != 0 ? 1u : 0u);
-            if (t + 1 == n_kv) ptx::umma_commit_a(bar_a + B_OFULL + g * 8);  // the item's O_g is complete (one phase per item)
-            // S_g(t+1) overwrites S_g(t) / P_g(t): the tensor pipe executes it after the PV above (same issuing thread)
-            if (t + 1 < n_kv) {
-              issue_s(g, gt0 + t + 1);
-              if (t + 2 == n_kv) ptx::umma_commit_a(bar_a + B_QEMPTY + g * 8);  // last S of the item: Q_g may be overwritten
-            }
-            done += 1u << (16 * g);
+            for (int kk = 0; kk < BKV / 16; ++kk)
+              ptx::umma_bf16_ts(tmem_base + 256 + g * 64, tmem_base + 384 + g * 64 + kk * 8,
+                                ptx::sw128_desc_from_lo(dv + kk * (2048 >> 4)), idesc_o, (t | kk) != 0 ? 1u : 0u);
+            ptx::umma_commit_a(bar_a + B_OFULL + g * 8);  // PV_g retired: P_g may be rewritten / O_g rescaled / (last tile) read
             tpar ^= 1u << g;
-            // the stage of tile t is free once both groups' MMAs on it retire; the group that issues last commits
-            if (ng == 1 || (int)((done >> (16 * (g ^ 1))) & 0xffffu) > t) ptx::umma_commit_a(bar_a + B_KVEMPTY + st * 8);
+            pp[g] = advance(g, pos);
+            // the stage is free once every group that works on the item has issued its PV on it: the one that comes last commits
+            if (!has_group(g ^ 1, (int)(pos >> 8)) || pp[g ^ 1] > pos) ptx::umma_commit_a(bar_a + B_KVEMPTY + st * 8);
           }
         }
-        gt0 += n_kv;
-        ipar ^= ng == 2 ? 3u : 1u;
       }
     }
   } else {
@@ -430,7 +459,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
     const int stid = tid & (GROUP_THREADS - 1);
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tmem_s = tmem_base + g * 128, tmem_o = tmem_base + 256 + g * 64;
+    const uint32_t tmem_s = tmem_base + g * 128, tmem_o = tmem_base + 256 + g * 64, tmem_p = tmem_base + 384 + g * 64;
     const uint32_t tab_a = smem_a + OFF_TAB + g * TAB_BYTES;
     const uint32_t win_a = tab_a + TAB_WIN, mask_a = tab_a + TAB_MASK, pmax_a = tab_a + TAB_PMAX;
     const bool has_pad = a.key_pad != nullptr;
@@ -440,7 +469,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     const int bar_id = 1 + g;
     // barrier addresses are derived from bar_a (32-bit shared address); par: bit 0 = item parity, bit 1 = tile parity
     const uint32_t bar_a = smem_a + OFF_BAR + g * 8;
-    constexpr uint32_t B_SFULL = 160, B_PFULL = 176, B_OFULL = 192, B_OFREE = 208;
+    constexpr uint32_t B_SFULL = 160, B_PFULL = 176, B_OFULL = 192, B_OFREE = 208, B_SFREE = 240;
     uint32_t par = 0;
 
     // table entries of a tile: thread stid < 255 owns entry stid of the bias window, thread stid < 128 one mask entry
@@ -449,13 +478,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       const int rel = t * BKV - q0 - 127 + stid;  // j - i
       return (stid < 255 && rel > -N && rel < N) ? __ldg(a.bias_vec + (it.h * (2 * N - 1) + (N - 1) + rel)) : 0.f;
     };
-    auto fetch_dead = [&](const Item& it, int t) -> bool {
+    // bit 0: the key is dead (past the end of the clip, or padded) -> -inf in the mask table; bit 1: it is dead because of the
+    // padding mask -- only that forces the masked path, the end of the clip is handled by the ragged fast path
+    auto fetch_dead = [&](const Item& it, int t) -> int {
       const int j = t * BKV + stid;
-      bool dead = j >= N;
-      if (stid < BKV && !dead && has_pad) dead = a.key_pad[(size_t)it.b * N + j] != 0;
+      int dead = j >= N ? 1 : 0;
+      if (stid < BKV && !dead && has_pad && a.key_pad[(size_t)it.b * N + j] != 0) dead = 3;
       return dead;
     };
-    auto store_tables = [&](uint32_t slot, float bv, bool dead) {
+    auto store_tables = [&](uint32_t slot, float bv, int dead) {
       const uint32_t wbuf = win_a + slot * WIN_FLOATS * 4;
       if (stid < 255) {
         bv *= LOG2E;  // exp2 domain; scaled here so that the global load stays in flight across the tile
@@ -470,18 +501,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     // ORs its `dead` flags: a tile without a padded / out-of-range key runs the unmasked fast path even when a padding
     // mask was passed (the production pipeline always passes one; it is mostly false).
     bool have_tab = false;
-    bool tile_dead = false;  // the tile about to be processed holds a dead key (group-uniform)
+    bool tile_dead = false;  // the tile about to be processed holds a PADDED key (group-uniform): masked path
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const Item it = decode_item(item, npairs, a.H, N);
       if (g == 1 && !it.has_b) continue;
       const int q0 = it.q0 + g * BQ, b = it.b, h = it.h;
       if (!have_tab) {
-        const bool dead0 = fetch_dead(it, 0);
+        const int dead0 = fetch_dead(it, 0);
         store_tables((par >> 1) & 1, fetch_bias(it, 0), dead0);
-        tile_dead = named_bar_or(bar_id, GROUP_THREADS, dead0 && stid < BKV);  // tables of the first tile are visible
+        tile_dead = named_bar_or(bar_id, GROUP_THREADS, (dead0 & 2) && stid < BKV);  // tables of the first tile are visible
       }
-      const float grep_a = __ldg(a.grep_a + h);  // 12 floats: an L1/L2 hit, consumed after the first S wait
+      // gate of this query row (from UNscaled q, backbone.py:544-550), precomputed by the QKV epilogue: in flight until S(0) lands
+      const float gate = q0 + r < N ? __ldg(a.gate + ((size_t)b * N + q0 + r) * a.H + h) : 0.f;
 
       // first tile that holds a valid key (0 unless the clip starts with >= 128 padded keys): group-uniform
       int jc_first = 0;  // first valid key rounded down to its 16-key chunk: tile = jc_first / 128, chunk column = jc_first % 128
@@ -498,18 +530,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       }
 
       have_tab = false;
-      float gate = 0.f;  // set on the item's first tile
 
       // m_run: reference max of the row (log2 domain).  An estimate on tile t_first (score_est); afterwards it only moves
       // (between tiles) when a tile's max exceeds it by more than RESCALE_THRESHOLD -- O and l are rescaled by
       // `pending` at the start of the next tile.  The result is exact after the final 1/l for any reference.
       float m_run = -INFINITY, l_run = 0.f, pending = 1.0f;
-      bool tab_dead = false;  // this thread's `dead` flag of the next item's first tile (stored on the last tile)
+      int tab_dead = 0;  // this thread's `dead` flags of the next item's first tile (stored on the last tile)
       for (int t = 0; t < n_kv; ++t) {
         const bool masked = tile_dead;
+        const int nv = N - t * BKV;                  // valid keys of this tile when it is the clip's last
+        const bool ragged = !masked && nv < BKV;
         const bool more = t + 1 < n_kv;
         float nbias = 0.f;
-        bool ndead = false;
+        int ndead = 0;
         if (more) {  // global loads in flight during the tile
           nbias = fetch_bias(it, t + 1);
           ndead = fetch_dead(it, t + 1);
@@ -527,44 +560,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const uint32_t mrow = mask_a + (slot * BKV + ch * 64) * 4;
         ptx::mbar_wait_a(bar_a + B_SFULL, slot);
         ptx::tc_fence_after();
-        if (t == 0) {
-          // gate of this query row from UNscaled q (backbone.py:544-550): the logits q.w_a, q.w_b were formed by the
-          // tensor core next to S_g(0) (hi and lo halves of w in columns 0,1 and 2,3); both column halves of the row
-          // read the same values: gate = sig_a * (sig_b * grep_a - 1) + 2
-          uint32_t z[4];
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(z[0]), "=r"(z[1]), "=r"(z[2]), "=r"(z[3])
-                       : "r"(tmem_base + 384 + g * 16 + lane_addr)
-                       : "memory");
-          ptx::tmem_ld_wait();
-          const float za = __uint_as_float(z[0]) + __uint_as_float(z[2]) + lds32(smem_a + OFF_GATEB);
-          const float zb = __uint_as_float(z[1]) + __uint_as_float(z[3]) + lds32(smem_a + OFF_GATEB + 4);
-          const float ga = 1.0f / (1.0f + __expf(-za)), gb = 1.0f / (1.0f + __expf(-zb));
-          gate = ga * (gb * grep_a - 1.0f) + 2.0f;
-        }
         if (t == jc_first / BKV) {
-          // Reference estimate from a 16-key chunk that holds a valid key.  Both column halves of the row read the SAME
-          // chunk, and the other half's warp may already be writing P over its first 32 columns: only chunks in columns
-          // 32..63 / 96..127 of S (never covered by P) can be read by both; otherwise the owning half reads and shares.
-          int c = jc_first % BKV;
-          bool shared_est = false;
-          if (!(c & 32)) {
-            if (!masked || lds32(mask_a + (slot * BKV + 32) * 4) == 0.f) c = 32;
-            else if (lds32(mask_a + (slot * BKV + 96) * 4) == 0.f) c = 96;
-            else shared_est = true;
-          }
+          // Reference estimate from the 16-key chunk that holds the clip's first valid key.  Both column halves of the row read
+          // the SAME chunk of S (nothing overwrites S_g(t) before both have delivered P_g(t)), so they agree without an exchange.
+          const int c = jc_first % BKV;
+          const bool est_masked = masked || ragged;  // the mask table also carries -inf for keys past the end of the clip
           const uint32_t ta = tmem_s + lane_addr + c, wa = wrow + (c - ch * 64) * 4, ma = mask_a + (slot * BKV + c) * 4;
-          if (!shared_est || ch == (c >> 6))
-            m_run = masked ? score_est<true>(ta, wa, ma, gate, qk_scale) : score_est<false>(ta, wa, ma, gate, qk_scale);
-          if (shared_est) {  // group-uniform (the mask is per key)
-            if (ch == (c >> 6)) sts32(pmax_a + (768 + r) * 4, m_run);
-            named_bar_sync(bar_id, GROUP_THREADS);
-            m_run = lds32(pmax_a + (768 + r) * 4);
-          }
+          m_run = est_masked ? score_est<true>(ta, wa, ma, gate, qk_scale) : score_est<false>(ta, wa, ma, gate, qk_scale);
         }
-        // O is only touched here when the reference moved (rare).  No barrier is needed: S_g(t) was issued after PV_g(t-1)
-        // and its commit (s_full, waited for above) covers every earlier MMA of the issuing thread, so O is consistent.
+        // O is only touched here when the reference moved (rare): PV_g(t-1) must have retired first (S_g(t) was issued ahead
+        // of it, so s_full does not cover it)
         if (t > 0 && __any_sync(0xffffffffu, pending != 1.0f)) {
+          ptx::mbar_wait_a(bar_a + B_OFULL, slot ^ 1);
+          ptx::tc_fence_after();
           {
             l_run *= pending;
 #pragma unroll 1
@@ -582,8 +590,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         }
         const float m_eff = m_run == -INFINITY ? 0.f : m_run;  // -inf only while every key so far was masked (p = 0)
         float mx, sum;
-        if (masked) stream_tile<true>(taddr, wrow, mrow, gate, qk_scale, m_eff, mx, sum);
-        else stream_tile<false>(taddr, wrow, mrow, gate, qk_scale, m_eff, mx, sum);
+        const uint32_t paddr = tmem_p + lane_addr + ch * 32, pvb = bar_a + B_OFULL;
+        const uint32_t sfb = bar_a + B_SFREE;
+        if (masked) stream_tile<TILE_MASKED>(taddr, paddr, pvb, slot ^ 1, sfb, lane, wrow, mrow, gate, qk_scale, m_eff, ch * 64, nv, mx, sum);
+        else if (ragged) stream_tile<TILE_RAGGED>(taddr, paddr, pvb, slot ^ 1, sfb, lane, wrow, mrow, gate, qk_scale, m_eff, ch * 64, nv, mx, sum);
+        else stream_tile<TILE_PLAIN>(taddr, paddr, pvb, slot ^ 1, sfb, lane, wrow, mrow, gate, qk_scale, m_eff, ch * 64, nv, mx, sum);
         l_run += sum;
         ptx::tc_fence_before();  // P is in TMEM (tcgen05.wait::st done): order it before the arrive
         __syncwarp();
@@ -594,7 +605,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         if (more) {
           sts32(pmax_a + ((slot * 2 + ch) * 128 + r) * 4, mx);
           store_tables(slot ^ 1, nbias, ndead);
-          tile_dead = named_bar_or(bar_id, GROUP_THREADS, ndead && stid < BKV);
+          tile_dead = named_bar_or(bar_id, GROUP_THREADS, (ndead & 2) && stid < BKV);
           const float m_tile = fmaxf(mx, lds32(pmax_a + ((slot * 2 + (ch ^ 1)) * 128 + r) * 4));
           if (m_run != -INFINITY && m_tile > m_run + RESCALE_THRESHOLD) {
             pending = ex2(m_run - m_tile);
@@ -608,10 +619,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
 
       // ---- finalise: O / l -> bf16 -------------------------------------------------------------------------------
       sts32(pmax_a + (512 + ch * 128 + r) * 4, l_run);
-      tile_dead = named_bar_or(bar_id, GROUP_THREADS, have_tab && tab_dead && stid < BKV);  // next item's first tile, if stored
+      tile_dead = named_bar_or(bar_id, GROUP_THREADS, have_tab && (tab_dead & 2) && stid < BKV);  // next item's first tile, if stored
       const float l_tot = l_run + lds32(pmax_a + (512 + (ch ^ 1) * 128 + r) * 4);
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-      ptx::mbar_wait_a(bar_a + B_OFULL, par & 1);  // the item's last PV has retired
+      ptx::mbar_wait_a(bar_a + B_OFULL, ((par >> 1) & 1) ^ 1);  // the item's last PV has retired (one phase per tile)
       ptx::tc_fence_after();
       uint32_t o[32];
       ptx::tmem_ld_32x32(tmem_o + lane_addr + ch * 32, o);
@@ -663,18 +674,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   }
 }
 
-}  // namespace
-}  // namespace avexk
+// gate[(b, n), h] = sig_a * (sig_b * grep_a[h] - 1) + 2 with (sig_a, sig_b) = sigmoid(q . gate_w[0|1] + gate_b[0|1]) from the bf16 q of
+// a qkv buffer: the stand-alone form of what the QKV GEMM epilogue computes from its fp32 accumulators inside avexk_beats_forward.
+__global__ void __launch_bounds__(256)
+gate_from_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, long long M, int H, const float* __restrict__ gate_w,
+                     const float* __restrict__ gate_b, const float* __restrict__ grep_a, float* __restrict__ gate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, head)
+  if (idx >= M * H) return;
+  const int h = idx % H;
+  const long long row = idx / H;
+  const uint4* q = reinterpret_cast<const uint4*>(qkv + row * (3LL * H * HD) + h * HD);
+  float za = gate_b[0], zb = gate_b[1];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    const uint4 u = __ldg(q + i);
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[j]));
+      const int c = i * 8 + j * 2;
+      za = fmaf(f.x, gate_w[c], za);
+      za = fmaf(f.y, gate_w[c + 1], za);
+      zb = fmaf(f.x, gate_w[HD + c], zb);
+      zb = fmaf(f.y, gate_w[HD + c + 1], zb);
+    }
+  }
+  const float ga = 1.0f / (1.0f + __expf(-za)), gb = 1.0f / (1.0f + __expf(-zb));
+  gate[idx] = ga * (gb * grep_a[h] - 1.0f) + 2.0f;
+}
 
-extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const float* gate_w, const float* gate_b,
-                                     const float* grep_a, const float* bias_vec, const uint8_t* key_pad, void* out,
-                                     void* stream) {
-  using namespace avexk;
-  AVEXK_CHECK_ARG(qkv && gate_w && gate_b && grep_a && bias_vec && out, "avexk_attention_gated: null argument");
-  AVEXK_CHECK_ARG(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535 && (long long)H * (2LL * N - 1) < (1LL << 31),
-                  "avexk_attention_gated: bad shape B=%d N=%d H=%d", B, N, H);
-  AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-                  "avexk_attention_gated: qkv/out must be 16-byte aligned");
+}  // namespace
+
+int launch_gate_from_qkv(const void* qkv, long long M, int H, const float* gate_w, const float* gate_b, const float* grep_a,
+                         float* gate, cudaStream_t st) {
+  if (M == 0) return AVEXK_OK;
+  gate_from_qkv_kernel<<<ceil_div(M * H, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), M, H, gate_w, gate_b, grep_a, gate);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+// qkv [B*N, 3*H*64] bf16, gate [B*N, H] fp32 (per-row gate of the relative-position bias), out [B*N, H*64] bf16
+int attention_launch(const void* qkv, int B, int N, int H, const float* gate, const float* bias_vec, const uint8_t* key_pad, void* out,
+                     cudaStream_t st) {
   if (B == 0) return AVEXK_OK;
   static bool attr_set[64] = {};  // per device: the opt-in is a per-device function attribute
   const int dev_ = current_device();
@@ -691,13 +732,35 @@ extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const
   rc = make_tmap_2d_64B(&map_out, out, (long long)B * N, (long long)H * HD, (long long)H * HD, 2, 32);
   if (rc) return rc;
   const long long items = (long long)B * H * ceil_div(N, 2 * BQ);
-  AVEXK_CHECK_ARG(items < (1LL << 31), "avexk_attention_gated: too many work items");
-  AttnTcArgs a{B, N, H, (int)items, gate_w, gate_b, grep_a, bias_vec, key_pad, reinterpret_cast<__nv_bfloat16*>(out)};
+  AVEXK_CHECK_ARG(items < (1LL << 31), "attention: too many work items");
+  AttnTcArgs a{B, N, H, (int)items, gate, bias_vec, key_pad, reinterpret_cast<__nv_bfloat16*>(out)};
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   prof_begin(st, KID_ATTN, 4.0 * B * H * (double)N * N * HD);
   attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, map_out, a);
   prof_end(st);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
+}
+
+}  // namespace avexk
+
+extern "C" int avexk_attention_gated(const void* qkv, int B, int N, int H, const float* gate_w, const float* gate_b,
+                                     const float* grep_a, const float* bias_vec, const uint8_t* key_pad, void* out,
+                                     void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(qkv && gate_w && gate_b && grep_a && bias_vec && out, "avexk_attention_gated: null argument");
+  AVEXK_CHECK_ARG(B >= 0 && N > 0 && H > 0 && H <= 65535 && B <= 65535 && (long long)H * (2LL * N - 1) < (1LL << 31),
+                  "avexk_attention_gated: bad shape B=%d N=%d H=%d", B, N, H);
+  AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  "avexk_attention_gated: qkv/out must be 16-byte aligned");
+  if (B == 0) return AVEXK_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // building-block entry: the per-row gates get a stream-ordered temporary (avexk_beats_forward keeps them in its workspace,
+  // written by the QKV GEMM epilogue)
+  float* gate = nullptr;
+  AVEXK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&gate), (size_t)B * N * H * sizeof(float), st));
+  int rc = launch_gate_from_qkv(qkv, (long long)B * N, H, gate_w, gate_b, grep_a, gate, st);
+  if (rc == AVEXK_OK) rc = attention_launch(qkv, B, N, H, gate, bias_vec, key_pad, out, st);
+  cudaFreeAsync(gate, st);
+  return rc;
 }

@@ -98,6 +98,8 @@ size_t workspace_bytes(const avexk_beats_dims& d, int B, int T, int precision = 
   s += al(M * Ff * 2);                  // h
   s += al(M * C * 4);                   // tmp: pre-LN sums (pos-conv; GEMM epilogues when the LayerNorm is not fused)
   s += al((long long)gemm_ln_scratch_bytes((int)M));  // fused GEMM+LayerNorm: per-CTA tiles, row statistics, counters
+  s += al((long long)(d.layers + 2) * B * C * 8);     // 40.24 fixed-point column sums of the fused mean-pooling (hooks + final)
+  s += al(M * d.heads * 4);                           // per-(token, head) gate of the relative-position bias (QKV epilogue -> attention)
   if (precision == 1) {
     s += al(M * 3 * C * 2);   // xs   [hi|lo|hi] of x
     s += al(M * 3 * C * 4);   // qkv  fp32
@@ -226,12 +228,12 @@ extern "C" int avexk_beats_set_precision(avexk_beats_t* h, int fp32_mode) {
 
 extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, int T, long long wav_stride,
                                    const avexk_fbank_t* fbank, const uint8_t* key_pad, const float* bias_vec, float* out,
-                                   float* const* hook_out, float* pooled, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+                                   float* const* hook_out, float* const* hook_pooled, float* pooled, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   using namespace avexk;
   AVEXK_CHECK_ARG(h && h->loaded, "avexk_beats_forward: weights not loaded");
   AVEXK_CHECK_ARG(wav && fbank && bias_vec && workspace, "avexk_beats_forward: null argument");
-  AVEXK_CHECK_ARG(out || pooled || hook_out, "avexk_beats_forward: no output requested");
+  AVEXK_CHECK_ARG(out || pooled || hook_out || hook_pooled, "avexk_beats_forward: no output requested");
   const avexk_beats_dims& d = h->d;
   const int N = avexk_beats_num_tokens(T);
   AVEXK_CHECK_ARG(B > 0 && N > 0, "avexk_beats_forward: clip too short (B=%d T=%d -> %d tokens)", B, T, N);
@@ -256,8 +258,15 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   float* tmp = cw.take<float>((size_t)M * C);
   const size_t ln_ws_bytes = gemm_ln_scratch_bytes((int)M);
   char* ln_ws = cw.take<char>(ln_ws_bytes);
+  long long* pool_acc = cw.take<long long>((size_t)(d.layers + 2) * B * C);  // [layers + 1 hooks | final][B][C]
+  float* gate = cw.take<float>((size_t)M * d.heads);
   AVEXK_CHECK_ARG(cw.ok, "avexk_beats_forward: workspace carve failed");
   float* x0 = (hook_out && hook_out[0]) ? hook_out[0] : x0_ws;
+  auto hpool = [&](int i) -> float* { return hook_pooled ? hook_pooled[i] : nullptr; };
+  // mean-pooling fused into the GEMM+LayerNorm epilogue (column sums per clip, no pass over [M,C]) needs the fused epilogue and
+  // at least one 32-row box per clip; otherwise the tensor is materialised and pooled by mean_pool_kernel
+  bool any_pool = pooled != nullptr;
+  for (int i = 0; i <= d.layers && hook_pooled; ++i) any_pool = any_pool || hook_pooled[i] != nullptr;
 
   int rc;
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
@@ -270,14 +279,17 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   // with the TMEM-resident LayerNorm epilogue: 33.1 ms (1) vs 32.8 ms (2) per step.
   static const int fuse_level = [] { const char* e = getenv("AVEXK_FUSE_LN"); return e ? atoi(e) : 2; }();
   const bool fuse_ln = C == 768 && fuse_level > 0;
+  const bool fuse_pool = fuse_ln && N >= 32 && h->precision != 1;
+  if (any_pool && fuse_pool) AVEXK_CUDA(cudaMemsetAsync(pool_acc, 0, (size_t)(d.layers + 2) * B * C * sizeof(long long), st));
   int ln_first = 1;  // the scratch counters are zeroed once per forward; every launch leaves them zero
+  // pool_raw / pool_y: fixed-point accumulators of the fused pooling (column sums of the raw Linear output / of the LN output)
   auto gemm_ln = [&](const void* A, int K, const __nv_bfloat16* W, const float* bias, float* raw, const float* gamma, const float* beta,
-                     float* dst_f32, __nv_bfloat16* dst_bf16) -> int {
+                     float* dst_f32, __nv_bfloat16* dst_bf16, long long* pool_raw, long long* pool_y) -> int {
     if (fuse_ln && (fuse_level >= 2 || K > C)) {
       const int zero = ln_first;
       ln_first = 0;
       return gemm_bf16_ln_launch(A, K, W, K, (int)M, K, bias, raw, x, alpha, gamma, beta, d.ln_eps, dst_f32, dst_bf16, ln_ws, ln_ws_bytes,
-                                 zero, st);
+                                 zero, st, pool_raw, pool_y, N);
     }
     int r = gemm_bf16_launch(A, K, W, K, (int)M, C, K, bias, 0, raw, x, alpha, tmp, C, 0, st);
     if (r) return r;
@@ -292,6 +304,7 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   TRY(gemm(peb, 3 * E, h->proj_w, C, h->proj_b, 0, nullptr, nullptr, 0.f, x0, 0));
   // ---- encoder prologue: mask, pos-conv + GELU + residual, LN (backbone.py:169-177) ------------------------------
   TRY(launch_group_pad(x0, key_pad, M, G, C / G, xg, st));
+  if (hpool(0)) TRY(launch_mean_pool(x0, nullptr, 0, B, N, C, hpool(0), st));  // hooks pool over ALL tokens (base_model.py:419-453)
   if (h->precision != 1) {
     TRY(launch_posconv(xg, h->posconv_w, h->posconv_b, x0, tmp, B, N, G, C / G, d.conv_pos, st));
     TRY(launch_layernorm(tmp, (int)M, C, h->enc_ln_w, h->enc_ln_b, d.ln_eps, x, xb, st));
@@ -322,7 +335,9 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
       TRY(gemm3(xs, 3 * C, L.fc1_w3, Ff, L.fc1_b, 1, nullptr, nullptr, h32));
       TRY(launch_split3_rows(h32, M, Ff, hs, st));
       float* raw = hook_out ? hook_out[li + 1] : nullptr;
+      if (!raw && hpool(li + 1)) raw = qkv32;  // free by now: scratch for the raw fc2 output that is pooled below
       TRY(gemm3(hs, 3 * Ff, L.fc2_w3, C, L.fc2_b, 0, raw, x, tmp));
+      if (hpool(li + 1)) TRY(launch_mean_pool(raw, nullptr, 0, B, N, C, hpool(li + 1), st));
       float* dst = (last && out) ? out : x;
       TRY(launch_layernorm(tmp, (int)M, C, L.ln2_w, L.ln2_b, d.ln_eps, dst, last ? nullptr : xs, st, 1));
       if (last && pooled) TRY(launch_mean_pool(dst, key_pad, key_pad != nullptr, B, N, C, pooled, st));
@@ -333,14 +348,25 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
   for (int li = 0; li < d.layers; ++li) {
     const avexk_beats::Layer& L = h->layers[li];
     const bool last = li == d.layers - 1;
-    TRY(gemm(xb, C, L.qkv_w, 3 * C, L.qkv_b, 0, nullptr, nullptr, 0.f, qkv, 1));
-    TRY(avexk_attention_gated(qkv, B, N, H, L.gate_w, L.gate_b, L.grep_a, bias_vec, key_pad, att, stream));
-    TRY(gemm_ln(att, C, L.o_w, L.o_b, nullptr, L.ln1_w, L.ln1_b, x, xb));
+    const GemmGate gg{L.gate_w, L.gate_b, L.grep_a, gate, H};  // the gates leave the QKV epilogue with q still in fp32
+    TRY(gemm_bf16_launch(xb, C, L.qkv_w, C, (int)M, 3 * C, C, L.qkv_b, 0, nullptr, nullptr, 0.f, qkv, 3 * C, 1, st, &gg));
+    TRY(attention_launch(qkv, B, N, H, gate, bias_vec, key_pad, att, st));
+    TRY(gemm_ln(att, C, L.o_w, L.o_b, nullptr, L.ln1_w, L.ln1_b, x, xb, nullptr, nullptr));
     TRY(gemm(xb, C, L.fc1_w, Ff, L.fc1_b, 1, nullptr, nullptr, 0.f, hb, 1));
     float* raw = hook_out ? hook_out[li + 1] : nullptr;
-    float* dst = (last && out) ? out : x;
-    TRY(gemm_ln(hb, Ff, L.fc2_w, L.fc2_b, raw, L.ln2_w, L.ln2_b, dst, last ? nullptr : xb));
-    if (last && pooled) {
+    float* hp = hpool(li + 1);
+    long long* acc_raw = (hp && fuse_pool) ? pool_acc + (size_t)li * B * C : nullptr;
+    if (hp && !fuse_pool && !raw) raw = reinterpret_cast<float*>(qkv);  // scratch (free by now): M x 3C bf16 >= M x C fp32
+    // final features: written only when the caller wants them, or when a masked mean-pool has to re-read them; the plain
+    // mean-pool of the last layer is a by-product of its LayerNorm epilogue
+    const bool pool_fused = last && pooled && fuse_pool && key_pad == nullptr;
+    long long* acc_y = pool_fused ? pool_acc + (size_t)(d.layers + 1) * B * C : nullptr;
+    float* dst = last ? (out ? out : ((pooled && !pool_fused) || !fuse_ln ? x : nullptr)) : x;
+    TRY(gemm_ln(hb, Ff, L.fc2_w, L.fc2_b, raw, L.ln2_w, L.ln2_b, dst, last ? nullptr : xb, acc_raw, acc_y));
+    if (acc_raw) TRY(launch_pool_finalize(acc_raw, B, C, 1.0f / N, hp, st));
+    else if (hp) TRY(launch_mean_pool(raw, nullptr, 0, B, N, C, hp, st));
+    if (acc_y) TRY(launch_pool_finalize(acc_y, B, C, 1.0f / N, pooled, st));
+    else if (last && pooled) {
       // any_pad is decided on the host by the caller passing key_pad == NULL when nothing is padded
       TRY(launch_mean_pool(dst, key_pad, key_pad != nullptr, B, N, C, pooled, st));
     }

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -85,5 +86,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+
+// fp16 storage of bounded activations (EfficientNet path, pos-conv operands): three more mantissa bits than bf16 at the same
+// tensor-core rate; values beyond the fp16 range saturate instead of becoming inf
+__device__ __forceinline__ uint32_t pack_h16(float lo, float hi) {
+  const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_h16(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 
 }  // namespace avexk

@@ -69,11 +69,6 @@ layernorm_kernel(const float* __restrict__ x, int M, const float* __restrict__ g
 // kind::f16 at the same rate for both formats, and the three extra mantissa bits matter -- the 6144-term pos-conv sum was the
 // largest single contributor to the end-to-end error of the bf16 path (tools/emulate_bf16.py: final max-abs 0.0196 -> 0.0039
 // on the perturbed-weights golden).  Values beyond the fp16 range saturate instead of becoming inf.
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-  return *reinterpret_cast<const uint32_t*>(&t);
-}
-
 __global__ void __launch_bounds__(256)
 group_pad_kernel(float* __restrict__ x0, const uint8_t* __restrict__ key_pad, long long M, int G, int cg,
                  __nv_bfloat16* __restrict__ xg) {
@@ -91,7 +86,7 @@ group_pad_kernel(float* __restrict__ x0, const uint8_t* __restrict__ key_pad, lo
       src[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const float4 a = src[0], b = src[1];
-      o = make_uint4(pack_f16(a.x, a.y), pack_f16(a.z, a.w), pack_f16(b.x, b.y), pack_f16(b.z, b.w));
+      o = make_uint4(pack_h16(a.x, a.y), pack_h16(a.z, a.w), pack_h16(b.x, b.y), pack_h16(b.z, b.w));
     }
   }
   reinterpret_cast<uint4*>(xg + (size_t)row * (G * 64) + g * 64)[ch] = o;
@@ -224,10 +219,37 @@ int launch_group_pad(float* x0, const uint8_t* key_pad, long long M, int G, int 
   return AVEXK_OK;
 }
 
+__global__ void pool_finalize_kernel(const long long* __restrict__ acc, long long n, float scale, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)((double)acc[i] * (1.0 / 16777216.0)) * scale;
+}
+
+int launch_pool_finalize(const long long* acc, int B, int C, float scale, float* out, cudaStream_t st) {
+  const long long n = (long long)B * C;
+  if (n == 0) return AVEXK_OK;
+  pool_finalize_kernel<<<ceil_div(n, 256), 256, 0, st>>>(acc, n, scale, out);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
 int launch_mean_pool(const float* x, const uint8_t* key_pad, int any_pad, int B, int N, int C, float* out, cudaStream_t st) {
   if (B == 0) return AVEXK_OK;
   dim3 grid(ceil_div(C, 256), B);
   mean_pool_kernel<<<grid, 256, 0, st>>>(x, key_pad, any_pad, N, C, out);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
+}
+
+int launch_f32_to_f16(const float* src, void* dst, long long n, cudaStream_t st) {
+  if (n == 0) return AVEXK_OK;
+  int grid = ceil_div(n, 256);
+  if (grid > 4096) grid = 4096;
+  f32_to_f16_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), n);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
 }

@@ -212,8 +212,12 @@ fbank_kernel(const float* __restrict__ wav, long long stride, int T, int F, int 
         const P2 x0 = make_float2(A.x, Bv.x), x1 = make_float2(A.y, Bv.y), x2 = make_float2(A.z, Bv.z), x3 = make_float2(A.w, Bv.w);
         const P2 d0 = pfmas(make_float2(pa, pb), -0.97f, x0), d1 = pfmas(x0, -0.97f, x1);  // beats.py:144
         const P2 d2 = pfmas(x1, -0.97f, x2), d3 = pfmas(x2, -0.97f, x3);
-        reinterpret_cast<float4*>(sD)[2 * u] = make_float4(d0.x, d0.y, d1.x, d1.y);
-        reinterpret_cast<float4*>(sD)[2 * u + 1] = make_float4(d2.x, d2.y, d3.x, d3.y);
+        // 16-byte unit e (two entries) lives at e ^ ((e >> 3) & 1): the eight lanes of a store phase write units 2u (then 2u+1)
+        // of two aligned groups of eight -- without the swizzle they would fall on the same banks pairwise; readers below fetch
+        // aligned groups of eight consecutive units, for which the swizzle is a per-lane constant
+        const int e0 = 2 * u, e1 = 2 * u + 1;
+        reinterpret_cast<float4*>(sD)[e0 ^ ((e0 >> 3) & 1)] = make_float4(d0.x, d0.y, d1.x, d1.y);
+        reinterpret_cast<float4*>(sD)[e1 ^ ((e1 >> 3) & 1)] = make_float4(d2.x, d2.y, d3.x, d3.y);
         const P2 ps = padd(padd(x0, x1), padd(x2, x3));
         sPS[u] = ps.x;
         if (u >= NQ - HOP / 4) sPS[u + HOP / 4] = ps.y;
@@ -245,12 +249,13 @@ fbank_kernel(const float* __restrict__ wav, long long stride, int T, int F, int 
 
     C2 v[16];
     {
-      const float4* dbase = reinterpret_cast<const float4*>(sD + HOP * flA);
+      // unit index 80 flA + 16 j + t: bit 3 of it is bit 3 of t, so the staging swizzle is `t ^ (t >> 3)` on the lane's offset
+      const float4* dbase = reinterpret_cast<const float4*>(sD + HOP * flA) + (t ^ (t >> 3));
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int n = t + 16 * j;  // complex point n = samples (2n, 2n+1)
         if (j < 12 || (j == 12 && t < 8)) {
-          const float4 d = dbase[n];  // (dA[2n], dB[2n], dA[2n+1], dB[2n+1])
+          const float4 d = dbase[16 * j];  // (dA[2n], dB[2n], dA[2n+1], dB[2n+1])
           const float2 w = *reinterpret_cast<const float2*>(sWin + 2 * n);
           v[j].re = pmuls(padd(make_float2(d.x, d.y), dc), w.x);  // beats.py:144,147
           v[j].im = pmuls(padd(make_float2(d.z, d.w), dc), w.y);
@@ -296,21 +301,25 @@ fbank_kernel(const float* __restrict__ wav, long long stride, int T, int F, int 
     {
       float2* xre = xg;
       float2* xim = xg + 8 * XROW;
+      // lane 0 is its own partner with the rows shifted by one (p pairs with 16-p): it publishes into the pad column 16 one
+      // row up, so that every lane reads row 7-p at column 16-t and the 16 addresses of a load fall on 16 distinct bank pairs
+      const bool l0 = t == 0;
+      const int wcol = l0 ? 16 - XROW : t;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        xre[i * XROW + t] = v[IDX16(8 + i)].re;
-        xim[i * XROW + t] = v[IDX16(8 + i)].im;
+        if (i > 0 || !l0) {
+          xre[i * XROW + wcol] = v[IDX16(8 + i)].re;
+          xim[i * XROW + wcol] = v[IDX16(8 + i)].im;
+        }
       }
       __syncwarp();
-      const bool l0 = t == 0;
-      const int srcl = (16 - t) & 15;
+      const int srcl = 16 - t;
       const C2 z8 = v[IDX16(8)];  // lane 0 needs its own Z[128] below
       C2 r[8];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int row = p == 0 ? 7 : (l0 ? 8 - p : 7 - p);
-        r[p].re = xre[row * XROW + srcl];
-        r[p].im = xim[row * XROW + srcl];
+      for (int p = 0; p < 8; ++p) {  // (p = 0 on lane 0 reads a stale slot and is replaced by A below)
+        r[p].re = xre[(7 - p) * XROW + srcl];
+        r[p].im = xim[(7 - p) * XROW + srcl];
       }
       __syncwarp();  // the exchange planes become the power spectrum
       float2* sP = xg;

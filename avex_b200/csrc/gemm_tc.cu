@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -93,7 +94,22 @@ struct GemmArgs {
   __nv_bfloat16* ln_out_bf16;
   float2* ln_stats;  // [ceil(M/256)*256][2*LN_NB] (sum, sum of squares) over 128 columns of a row
   int* ln_count;     // [2][2*ceil(M/256)]: arrivals / departures per 128-row block; zero before and after every launch
+  // column sums over the token rows of every clip (mean-pooled embeddings without a second pass over [M,768]):
+  // 40.24 fixed-point accumulators [M / pool_rows][768], so the atomics are order-independent and the result reproducible
+  // fused QKV projection: the gate of BEATs' relative-position bias from the q part of the output (columns < gate_heads * 64),
+  // gate[m, h] = sig_a (sig_b grep_a[h] - 1) + 2, (sig_a, sig_b) = sigmoid(q_h . gate_w[0|1] + gate_b[0|1]) (backbone.py:544-550),
+  // formed on the fp32 accumulators (+ bias) before they are rounded to bf16
+  const float* gate_w;   // [2, 64]
+  const float* gate_b;   // [2]
+  const float* grep_a;   // [heads]
+  float* gate_out;       // [M, heads] or null
+  int gate_heads;
+  long long* pool_raw;  // of v = A @ W^T + bias (the tensor a forward hook on the Linear sees), or null
+  long long* pool_y;    // of the LayerNorm output, or null
+  int pool_rows;        // token rows per clip (>= 32)
 };
+
+constexpr float POOL_FIX = 16777216.0f;  // 2^24
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
@@ -141,6 +157,42 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
 }
 __device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// Column sums of a 32 x 32 fp32 box staged in shared memory (128-byte rows, 16-byte chunk j of row r at chunk j ^ (r & 7)):
+// lane c reads column c of every row (one row = 32 banks: conflict-free) and adds the sum over the rows of each clip to that
+// clip's accumulator.  row0: first global row of the box; rows >= M are excluded; a box straddles at most one clip boundary
+// (pool_rows >= 32).
+__device__ __forceinline__ void pool_box(uint32_t box, int lane, int row0, int M, int pool_rows, long long* acc, int col) {
+  const int b0 = row0 / pool_rows;
+  const int lim = (b0 + 1) * pool_rows - row0;        // rows of clip b0 in this box (warp-uniform)
+  const int nval = M - row0 < 32 ? M - row0 : 32;     // valid rows (warp-uniform)
+  const uint32_t base = box + (lane & 3) * 4;
+  const int cj = lane >> 2;
+  float sa = 0.f, sb = 0.f;
+  if (nval == 32 && lim >= 32) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) sa += lds32f(base + r * 128 + ((cj ^ (r & 7)) << 4));
+  } else {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const float x = lds32f(base + r * 128 + ((cj ^ (r & 7)) << 4));
+      if (r < nval) {
+        if (r < lim) sa += x;
+        else sb += x;
+      }
+    }
+  }
+  if (nval > 0) atomicAdd(reinterpret_cast<unsigned long long*>(acc + (size_t)b0 * LN_C + col + lane),
+                          static_cast<unsigned long long>(__float2ll_rn(sa * POOL_FIX)));
+  if (nval > lim) atomicAdd(reinterpret_cast<unsigned long long*>(acc + (size_t)(b0 + 1) * LN_C + col + lane),
+                            static_cast<unsigned long long>(__float2ll_rn(sb * POOL_FIX)));
 }
 
 template <int MODE, bool PAIR, int EW, bool DEEPK>
@@ -254,7 +306,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     } else if (warp == 1 && (!PAIR || rank == 0)) {
       // ===================== MMA issuer (leader CTA of a pair) =====================
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(C::UM, BN);
+      constexpr uint32_t idesc = MODE == MODE_CONV ? ptx::make_idesc_f16(C::UM, BN) : ptx::make_idesc_bf16(C::UM, BN);  // EfficientNet: fp16
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -376,6 +428,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        if (ln && g.pool_raw != nullptr) {  // mean-pooled hook: column sums of the raw Linear output, via the (idle) output staging
+          if (lane == 0) ptx::tma_store_wait_read();  // pass 2 of the previous tile may still be reading the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128f(ybuf + rowoff + ((j ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          pool_box(ybuf, lane, row0, g.M, g.pool_rows, g.pool_raw, col0);
+          __syncwarp();
+        }
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -487,12 +548,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               sts128u(xbuf + lane * 64 + ((j ^ sw64) << 4), pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
                       pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
           }
-          if (g.ln_out_f32 != nullptr) {
+          if (g.ln_out_f32 != nullptr || g.pool_y != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) sts128f(ybuf + rowoff + ((j ^ sw) << 4), y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
           }
           ptx::fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
           __syncwarp();
+          if (g.pool_y != nullptr) pool_box(ybuf, lane, row0, g.M, g.pool_rows, g.pool_y, col0);  // mean-pool fused: no pass over y
           if (lane == 0) {  // rows >= M are clipped by the tensor maps
             if (g.ln_out_bf16 != nullptr) ptx::tma_store_2d_s(&map_xb, xbuf, col0, row0);
             if (g.ln_out_f32 != nullptr) ptx::tma_store_2d_s(&map_y, ybuf, col0, row0);
@@ -549,6 +611,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         else ptx::mbar_arrive(&tempty_bar[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      // the warp's 64 columns are one attention head of q: its two gate logits are dot products over them (warp-uniform test)
+      const bool do_gate = MODE == MODE_PLAIN && g.gate_out != nullptr && colb < g.gate_heads * 64;
+      float2 za2 = make_float2(0.f, 0.f), zb2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = colb + c * 32;
@@ -562,6 +627,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           v[4 * j + 1] = __uint_as_float(r[c][4 * j + 1]) + b4.y;
           v[4 * j + 2] = __uint_as_float(r[c][4 * j + 2]) + b4.z;
           v[4 * j + 3] = __uint_as_float(r[c][4 * j + 3]) + b4.w;
+        }
+        if (do_gate) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(g.gate_w + c * 32) + j);       // warp-uniform, L1-resident
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(g.gate_w + 64 + c * 32) + j);
+            za2 = __ffma2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(wa.x, wa.y), za2);
+            za2 = __ffma2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(wa.z, wa.w), za2);
+            zb2 = __ffma2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(wb.x, wb.y), zb2);
+            zb2 = __ffma2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(wb.z, wb.w), zb2);
+          }
         }
         if (MODE == MODE_GELU) {
 #pragma unroll
@@ -600,6 +676,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             flush_box(col0 + 16 * h2, row0);
           }
         }
+      }
+      if (do_gate && grow < g.M) {
+        const int hh = colb >> 6;
+        const float za = za2.x + za2.y + __ldg(g.gate_b), zb = zb2.x + zb2.y + __ldg(g.gate_b + 1);
+        const float ga = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * za)), gb = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * zb));
+        g.gate_out[(size_t)grow * g.gate_heads + hh] = ga * (gb * __ldg(g.grep_a + hh) - 1.0f) + 2.0f;
       }
     }
     if (lane == 0) ptx::tma_store_wait_all();  // the bulk stores must have been performed before the CTA exits
@@ -645,8 +727,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             if (g.res_bf16 != nullptr) {
               const uint2 rb = __ldg(reinterpret_cast<const uint2*>(g.res_bf16 + off));
-              const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.x));
-              const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rb.y));
+              const float2 r0 = unpack_h16(rb.x), r1 = unpack_h16(rb.y);  // the skip connection is stored as fp16
               v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
             }
           } else {
@@ -660,7 +741,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (g.out != nullptr) {
             const size_t oo = (size_t)grow * g.ldo + cc;
             if (g.out_bf16) {
-              uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+              uint2 pk = MODE == MODE_CONV ? make_uint2(pack_h16(v.x, v.y), pack_h16(v.z, v.w)) : make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
               *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.out) + oo) = pk;
             } else {
               *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + oo) = v;
@@ -810,11 +891,15 @@ int launch_any(const void* A, long long lda, const void* W, long long ldw, const
 
 int gemm_bf16_launch(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias, int gelu,
                      float* raw_out, const float* residual, float res_scale, void* out, long long ldo, int out_bf16,
-                     cudaStream_t st) {
+                     cudaStream_t st, const GemmGate* gate) {
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.raw_out = raw_out; g.residual = residual; g.res_scale = res_scale;
   g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16;
+  if (gate != nullptr) {
+    AVEXK_CHECK_ARG(!gelu && residual == nullptr && gate->heads * 64 <= N, "gemm: the gate epilogue belongs to the plain (QKV) flavour");
+    g.gate_w = gate->w; g.gate_b = gate->b; g.grep_a = gate->grep_a; g.gate_out = gate->out; g.gate_heads = gate->heads;
+  }
   if (gelu) {
     AVEXK_CHECK_ARG(residual == nullptr, "gemm: GELU and residual epilogues are exclusive");
     return launch_any<MODE_GELU>(A, lda, W, ldw, g, st);
@@ -849,7 +934,9 @@ size_t gemm_ln_scratch_bytes(int M) { return ln_scratch_layout(M).total; }
 int gemm_bf16_ln_launch(const void* A, long long lda, const void* W, long long ldw, int M, int K, const float* bias, float* raw_out,
                         const float* residual, float res_scale, const float* gamma, const float* beta, float eps,
                         float* ln_out_f32, __nv_bfloat16* ln_out_bf16, void* scratch, size_t scratch_bytes, int zero_counters,
-                        cudaStream_t st) {
+                        cudaStream_t st, long long* pool_raw, long long* pool_y, int pool_rows) {
+  AVEXK_CHECK_ARG((pool_raw == nullptr && pool_y == nullptr) || (pool_rows >= 32 && M % pool_rows == 0),
+                  "gemm+LN: fused pooling needs >= 32 token rows per clip and M a multiple of it (M=%d rows=%d)", M, pool_rows);
   const LnScratch L = ln_scratch_layout(M);
   AVEXK_CHECK_ARG(scratch != nullptr && scratch_bytes >= L.total && (reinterpret_cast<uintptr_t>(scratch) & 255) == 0,
                   "gemm+LN: scratch too small or misaligned");
@@ -861,6 +948,7 @@ int gemm_bf16_ln_launch(const void* A, long long lda, const void* W, long long l
   g.ln_gamma = gamma; g.ln_beta = beta; g.ln_eps = eps; g.ln_out_f32 = ln_out_f32; g.ln_out_bf16 = ln_out_bf16;
   g.ln_stats = reinterpret_cast<float2*>(base + L.stats);
   g.ln_count = reinterpret_cast<int*>(base + L.count);
+  g.pool_raw = pool_raw; g.pool_y = pool_y; g.pool_rows = pool_rows;
   return launch_any<MODE_RES>(A, lda, W, ldw, g, st);
 }
 
@@ -900,6 +988,33 @@ extern "C" int avexk_gemm_bf16(const void* A, long long lda, const void* W, long
 
 extern "C" size_t avexk_gemm_ln_scratch_bytes(int M) { return M > 0 ? avexk::gemm_ln_scratch_bytes(M) : 0; }
 
+extern "C" int avexk_gemm_bf16_ln_pooled(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                                         const float* bias, float* raw_out, const float* residual, float res_scale,
+                                         const float* gamma, const float* beta, float eps, float* out_f32, void* out_bf16,
+                                         void* scratch, size_t scratch_bytes, int rows_per_clip, float* pooled_raw,
+                                         float* pooled_y, void* pool_ws, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(A && W && gamma && beta && (out_f32 || out_bf16 || pooled_raw || pooled_y), "avexk_gemm_bf16_ln_pooled: null operand");
+  AVEXK_CHECK_ARG(N == LN_C, "avexk_gemm_bf16_ln_pooled: the fused LayerNorm epilogue is built for N = %d (got %d)", LN_C, N);
+  AVEXK_CHECK_ARG(M >= 0 && K > 0 && K % 8 == 0 && lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0,
+                  "avexk_gemm_bf16_ln_pooled: unsupported shape / leading dimensions");
+  AVEXK_CHECK_ARG((!pooled_raw && !pooled_y) || (pool_ws && rows_per_clip >= 32 && M % rows_per_clip == 0),
+                  "avexk_gemm_bf16_ln_pooled: pooling needs pool_ws and rows_per_clip >= 32 dividing M");
+  if (M == 0) return AVEXK_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nclips = rows_per_clip > 0 ? M / rows_per_clip : 0;
+  long long* acc_raw = pooled_raw ? reinterpret_cast<long long*>(pool_ws) : nullptr;
+  long long* acc_y = pooled_y ? reinterpret_cast<long long*>(pool_ws) + (size_t)nclips * LN_C : nullptr;
+  if (acc_raw || acc_y) AVEXK_CUDA(cudaMemsetAsync(pool_ws, 0, (size_t)2 * nclips * LN_C * sizeof(long long), st));
+  int rc = gemm_bf16_ln_launch(A, lda, W, ldw, M, K, bias, raw_out, residual, res_scale, gamma, beta, eps, out_f32,
+                               reinterpret_cast<__nv_bfloat16*>(out_bf16), scratch, scratch_bytes, 1, st, acc_raw, acc_y, rows_per_clip);
+  if (rc) return rc;
+  if (acc_raw) rc = launch_pool_finalize(acc_raw, nclips, LN_C, 1.0f / rows_per_clip, pooled_raw, st);
+  if (rc) return rc;
+  if (acc_y) rc = launch_pool_finalize(acc_y, nclips, LN_C, 1.0f / rows_per_clip, pooled_y, st);
+  return rc;
+}
+
 extern "C" int avexk_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
                                   float* raw_out, const float* residual, float res_scale, const float* gamma, const float* beta,
                                   float eps, float* out_f32, void* out_bf16, void* scratch, size_t scratch_bytes, void* stream) {
@@ -911,5 +1026,5 @@ extern "C" int avexk_gemm_bf16_ln(const void* A, long long lda, const void* W, l
   if (M == 0) return AVEXK_OK;
   return gemm_bf16_ln_launch(A, lda, W, ldw, M, K, bias, raw_out, residual, res_scale, gamma, beta, eps, out_f32,
                              reinterpret_cast<__nv_bfloat16*>(out_bf16), scratch, scratch_bytes, 1,
-                             reinterpret_cast<cudaStream_t>(stream));
+                             reinterpret_cast<cudaStream_t>(stream), nullptr, nullptr, 0);
 }

@@ -111,6 +111,12 @@ def make_model_class(base):
             x = self.process_audio(x)
             bk = self.backbone
             hooked = bk._hooked_layers()
+            if getattr(self, "_pool_hooks", False):
+                # extract_embeddings(aggregation="mean"): the hooked tensors leave the kernels already mean-pooled over the tokens
+                # ([B,768] per layer, a by-product of the fc2 epilogue); nothing of size [B,N,768] is written for them
+                res = bk.run(x, padding_mask, want_features=False, hook_layers=hooked, hook_pool=True)
+                bk._fire_hooks(res["hooks"])
+                return None
             if self._return_features_only:
                 res = bk.run(x, padding_mask, want_features=True, hook_layers=hooked)
                 bk._fire_hooks(res["hooks"])
@@ -146,8 +152,14 @@ def make_model_class(base):
             try:
                 self._clear_hook_outputs()
                 mask = x.get("padding_mask") if isinstance(x, dict) else padding_mask
-                with torch.no_grad():
-                    self.forward(wav, mask)
+                # "mean" over the token axis commutes with nothing downstream (aggregate_embeddings passes 2-D tensors through),
+                # so it is done on the device -- unless someone else's forward hooks would see the pooled tensors
+                self._pool_hooks = aggregation == "mean" and self.backbone.hooks_are_only(self._hooks.values())
+                try:
+                    with torch.no_grad():
+                        self.forward(wav, mask)
+                finally:
+                    self._pool_hooks = False
                 order = self._hook_layers if self._hook_layers else list(self._hook_outputs.keys())
                 embeddings = [self._hook_outputs[n] for n in order]
                 if not embeddings:

@@ -15,36 +15,93 @@ from .registry import get_model_class, get_model_spec, list_models
 logger = logging.getLogger(__name__)
 
 
+_HEAD_TERMS = ("classifier", "head", "classification", "classification_head")
+
+
 def _read_checkpoint(path: str) -> dict:
     if str(path).endswith(".safetensors"):
         from safetensors.torch import load_file
 
         return load_file(str(path), device="cpu")
     obj = torch.load(str(path), map_location="cpu", weights_only=True)
-    for key in ("model_state_dict", "state_dict", "model"):  # utils/utils.py:509-570 wrappers
-        if isinstance(obj, dict) and key in obj and isinstance(obj[key], dict):
-            obj = obj[key]
+    if isinstance(obj, dict):  # utils/utils.py:536-540 wrappers
+        if "model_state_dict" in obj:
+            obj = obj["model_state_dict"]
+        elif "model" in obj and isinstance(obj["model"], dict):
+            obj = obj["model"]
+        elif "state_dict" in obj and isinstance(obj["state_dict"], dict):
+            obj = obj["state_dict"]
     return obj
 
 
+def _map_key(key: str, keep_classifier: bool, drop_model_prefix: bool) -> Optional[str]:
+    """`_process_state_dict` (utils/utils.py:509-570) for one key: strip `module.` or (optionally) `model.`, drop head layers."""
+    if not keep_classifier and key in ("classifier.weight", "classifier.bias", "model.classifier.1.weight", "model.classifier.1.bias"):
+        return None
+    if key.startswith("module."):
+        key = key[7:]
+    elif drop_model_prefix and key.startswith("model."):
+        key = key[6:]
+    if not keep_classifier and any(t in key.lower() for t in _HEAD_TERMS):
+        return None
+    return key
+
+
+def _resolve_keys(keys, target_keys, keep_classifier: bool) -> dict:
+    """checkpoint key -> model key, with the `backbone.` prefix adapted either way (load.py:548-556)."""
+    drop_model = not any(k.startswith("model.") for k in target_keys)
+    mapped = {}
+    for k in keys:
+        m = _map_key(k, keep_classifier, drop_model)
+        if m is not None:
+            mapped[k] = m
+    wants = any(k.startswith("backbone.") for k in target_keys)
+    has = any(m.startswith("backbone.") for m in mapped.values())
+    if wants and not has:
+        mapped = {k: "backbone." + m for k, m in mapped.items()}
+    elif has and not wants:
+        mapped = {k: (m[len("backbone."):] if m.startswith("backbone.") else m) for k, m in mapped.items()}
+    return mapped
+
+
+def _stream_safetensors(model: torch.nn.Module, path: str, keep_classifier: bool):
+    """safetensors -> the model's (device) parameters, one tensor at a time straight from the memory-mapped file: the whole
+    checkpoint is never materialised as a CPU state dict (the reference reads everything, then `load_state_dict`s).
+    Same key handling and strict=False semantics as `_load_checkpoint`; returns (missing, unexpected)."""
+    from safetensors import safe_open
+
+    own = dict(model.state_dict(keep_vars=True))  # parameters and buffers, by name
+    seen, unexpected = set(), []
+    with safe_open(str(path), framework="pt", device="cpu") as f:
+        mapped = _resolve_keys(list(f.keys()), own.keys(), keep_classifier)
+        with torch.no_grad():
+            for ck, mk in mapped.items():
+                dst = own.get(mk)
+                if dst is None:
+                    unexpected.append(mk)
+                    continue
+                src = f.get_tensor(ck)
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise RuntimeError(f"size mismatch for {mk}: checkpoint {tuple(src.shape)} vs model {tuple(dst.shape)}")
+                dst.copy_(src, non_blocking=True)  # host (mmap) -> device, converted to the parameter's dtype
+                seen.add(mk)
+    for m in model.modules():  # in-place copies do not bump tensor versions: packed weight copies must be rebuilt
+        if hasattr(m, "invalidate"):
+            m.invalidate()
+    eng = getattr(model, "_engine", None)
+    if eng is not None and hasattr(eng, "invalidate"):
+        eng.invalidate()
+    return [k for k in own if k not in seen], unexpected
+
+
 def _load_checkpoint(model: torch.nn.Module, path: str, keep_classifier: bool) -> None:
-    """load.py:521-570: strip DDP prefixes, drop classifier keys in features-only mode, fix the `backbone.` prefix, strict=False."""
-    sd = {}
-    for k, v in _read_checkpoint(path).items():
-        for pre in ("module.", "model."):
-            if k.startswith(pre):
-                k = k[len(pre):]
-        if not keep_classifier and k.startswith(("classifier.", "head.")):
-            continue
-        sd[k] = v
-    target = set(model.state_dict().keys())
-    wants_prefix = any(k.startswith("backbone.") for k in target)
-    has_prefix = any(k.startswith("backbone.") for k in sd)
-    if wants_prefix and not has_prefix:
-        sd = {"backbone." + k: v for k, v in sd.items()}
-    elif has_prefix and not wants_prefix:
-        sd = {k[len("backbone."):] if k.startswith("backbone.") else k: v for k, v in sd.items()}
-    missing, unexpected = model.load_state_dict(sd, strict=False)
+    """load.py:521-570: unwrap, strip DDP prefixes, drop head keys in features-only mode, fix the `backbone.` prefix, strict=False."""
+    if str(path).endswith(".safetensors"):
+        missing, unexpected = _stream_safetensors(model, path, keep_classifier)
+    else:
+        raw = _read_checkpoint(path)
+        mapped = _resolve_keys(list(raw.keys()), model.state_dict().keys(), keep_classifier)
+        missing, unexpected = model.load_state_dict({m: raw[k] for k, m in mapped.items()}, strict=False)
     logger.info(f"Loaded checkpoint {path}: {len(missing)} missing, {len(unexpected)} unexpected keys")
 
 

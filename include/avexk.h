@@ -107,6 +107,15 @@ size_t avexk_gemm_ln_scratch_bytes(int M);
 int avexk_gemm_bf16_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
                        float* raw_out, const float* residual, float res_scale, const float* gamma, const float* beta, float eps,
                        float* out_f32, void* out_bf16, void* scratch, size_t scratch_bytes, void* stream);
+/* The same launch with mean-pooling over the token rows of every clip fused into the epilogue (the rows are M / rows_per_clip
+ * clips of rows_per_clip >= 32 consecutive rows): pooled_raw [clips,768] = mean of v (what `extract_embeddings(aggregation="mean")`
+ * reduces a hooked fc2 output to, base_model.py:419-453), pooled_y [clips,768] = mean of y (beats_model.py:275); either may be
+ * NULL, and y itself need not be written (out_f32 == out_bf16 == NULL).  Column sums are accumulated in 40.24 fixed point, so
+ * the result does not depend on the order of the atomics.  pool_ws: 2 * clips * 768 * 8 bytes. */
+int avexk_gemm_bf16_ln_pooled(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const float* bias,
+                              float* raw_out, const float* residual, float res_scale, const float* gamma, const float* beta,
+                              float eps, float* out_f32, void* out_bf16, void* scratch, size_t scratch_bytes, int rows_per_clip,
+                              float* pooled_raw, float* pooled_y, void* pool_ws, void* stream);
 /* Tuning knob: 1 (default) = CTA pairs (tcgen05 cta_group::2, 256x256 tiles), 0 = single-CTA 128x256 tiles.  Returns the
  * previous setting; any other argument only queries.  Environment override at first use: AVEXK_GEMM_PAIR=0. */
 int avexk_gemm_config(int pair);
@@ -200,10 +209,14 @@ size_t avexk_beats_workspace_bytes(const avexk_beats_t* h, int B, int T);
  *             [0]   post_extract_proj output [B,N,C] (rows of padded tokens zeroed, as the reference's in-place
  *                   `x[padding_mask] = 0` makes a hook see them, backbone.py:169-170)
  *             [i+1] raw fc2 output of block i [B,N,C]   (beats_model.py:206-227)
+ * hook_pooled HOST array of layers+1 DEVICE pointers [B,C] (NULL entry / NULL array = not wanted): the same tensors mean-pooled
+ *           over ALL tokens (what `extract_embeddings(aggregation="mean")` makes of a hook, base_model.py:419-453) without
+ *           materialising [B,N,C] -- a by-product of the fc2 epilogue (probes on layer-wise features)
  * pooled    [B,C] fp32 mean over tokens (masked mean when key_pad has padded tokens, beats_model.py:269-275); may be NULL. */
 int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, int T, long long wav_stride,
                         const avexk_fbank_t* fbank, const uint8_t* key_pad, const float* bias_vec, float* out,
-                        float* const* hook_out, float* pooled, void* workspace, size_t workspace_bytes, void* stream);
+                        float* const* hook_out, float* const* hook_pooled, float* pooled, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * STFT mel spectrogram of the EfficientNet path.
@@ -230,25 +243,27 @@ int avexk_melspec_forward(const avexk_melspec_t* h, const float* wav, int B, int
                           float* out, void* minmax_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * EfficientNet building blocks (NHWC bf16 activations) and the whole feature extractor
+ * EfficientNet building blocks (NHWC fp16 activations) and the whole feature extractor
  * (avex/models/efficientnet.py:163-215 -> torchvision efficientnet_b0/b1 .features / .avgpool / .classifier).
  * ---------------------------------------------------------------------------------------------------------- */
 
-/* 1x1 convolution == GEMM on the tcgen05 kernel: A [M,K] bf16 (NHWC rows), W [N,K] bf16 (conv weight [N,K,1,1]).
+/* The EfficientNet path stores activations and tensor-core operands as FP16 (bounded post-BatchNorm / SiLU values; same
+ * tensor-core rate as bf16, three more mantissa bits): "16" below means IEEE half.
+ * 1x1 convolution == GEMM on the tcgen05 kernel: A [M,K] fp16 (NHWC rows), W [N,K] fp16 (conv weight [N,K,1,1]).
  *   acc = A @ W^T ; raw_out[m,n] = acc (fp32, the pre-BatchNorm tensor a hook on the conv sees; may be NULL)
  *   y = acc * scale[n] + shift[n] (folded BatchNorm; scale NULL = 1) ; silu != 0: y = y * sigmoid(y)
- *   res_bf16 != NULL: y += res[m,n] (MBConv skip connection) ; out[m,n] = y as bf16 (out_bf16 != 0) or fp32.
+ *   res_f16 != NULL: y += res[m,n] (MBConv skip connection, fp16) ; out[m,n] = y as fp16 (out_f16 != 0) or fp32.
  * K and N must be multiples of 8. */
-int avexk_conv1x1_bf16(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
-                       const void* res_bf16, float* raw_out, void* out, int out_bf16, void* stream);
+int avexk_conv1x1_f16(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
+                      const void* res_f16, float* raw_out, void* out, int out_f16, void* stream);
 
 /* Depthwise k x k convolution (k = 3 | 5, stride 1 | 2, padding (k-1)/2) + folded BatchNorm + SiLU.
- * in [B,H,W,C] bf16, w_ckk [C,1,k,k] fp32 (torch layout), out [B,Ho,Wo,C] bf16, Ho = (H + 2p - k) / stride + 1.
+ * in [B,H,W,C] fp16, w_ckk [C,1,k,k] fp32 (torch layout), out [B,Ho,Wo,C] fp16, Ho = (H + 2p - k) / stride + 1.
  * se_sum [B,C] fp32 (may be NULL) receives sum over output pixels of the activated output (squeeze-excitation).
  * The sums are accumulated in 40.24 fixed point, so they are bit-reproducible from run to run.
  * workspace >= 8*B*C + 4*C*k*k bytes (fixed-point accumulators, repacked weights). */
-int avexk_dwconv_nhwc(const void* in_bf16, int B, int H, int W, int C, int k, int stride, const float* w_ckk,
-                      const float* scale, const float* shift, void* out_bf16, float* se_sum, void* workspace, void* stream);
+int avexk_dwconv_nhwc(const void* in_f16, int B, int H, int W, int C, int k, int stride, const float* w_ckk,
+                      const float* scale, const float* shift, void* out_f16, float* se_sum, void* workspace, void* stream);
 
 typedef struct avexk_effnet avexk_effnet_t;
 

@@ -90,6 +90,32 @@ def test_fp32_mode_against_reference_golden(cname):
     _cmp(f"bf16 again {cname}/final", feats16.cpu().numpy(), g["final"])
 
 
+def test_pooled_hooks_are_formed_on_device():
+    """`extract_embeddings(aggregation="mean")` gets its per-layer [B,768] means from the fc2 epilogues (nothing of
+    size [B,N,768] is written); they must equal the means of the materialised hooks, also under a padding mask (the reference
+    pools hooks over ALL tokens) -- and a foreign forward hook on a hooked module switches the shortcut off."""
+    case = cases.beats_cases()["L2_2x2s_mask"]
+    model, _ = _build(2, case["wseed"])
+    wav, mask = torch.from_numpy(case["wav"]).cuda(), torch.from_numpy(case["mask"]).cuda()
+    model.register_hooks_for_layers(["all"])
+    for m in (mask, None):
+        full = model.extract_embeddings(wav, padding_mask=m, aggregation="none")
+        want = torch.cat([h.mean(dim=1) for h in full], dim=1)
+        before = torch.cuda.max_memory_allocated()
+        got = model.extract_embeddings(wav, padding_mask=m, aggregation="mean")
+        assert got.shape == (2, 3 * 768)
+        assert (got - want).abs().max().item() <= 2e-5, (got - want).abs().max().item()
+        assert torch.cuda.max_memory_allocated() == before  # no [B,N,768] hook tensors were allocated
+    res = model.backbone.run(wav, None, want_features=False, hook_layers=[0, 1, 2], hook_pool=True)
+    assert all(t.shape == (2, 768) for t in res["hooks"].values())
+    seen = []
+    h = model.backbone.encoder.layers[1].fc2.register_forward_hook(lambda mod, inp, out: seen.append(tuple(out.shape)))
+    got2 = model.extract_embeddings(wav, aggregation="mean")
+    h.remove()
+    assert seen == [(96, 2, 768)]  # the user's hook saw the reference's (T, B, C) tensor, not a pooled one
+    assert (got2 - got).abs().max().item() <= 2e-5
+
+
 def test_classifier_mode_masked_mean_pool():
     case = cases.beats_cases()["L2_2x2s_mask"]
     from avex_b200 import plugin

@@ -123,6 +123,49 @@ def test_gemm_fused_layernorm(lib, pair, M, K, raw, inplace):
                                   beta.data_ptr(), 1e-5, None, o16b.data_ptr(), scratch.data_ptr(), 16, _stream()) != 0  # fmt: skip
 
 
+@pytest.mark.parametrize("clips,rows,K,want_y", [(4, 496, 768, True), (3, 40, 3072, False), (7, 2992, 3072, True), (33, 248, 768, False),
+                                                 (1, 32, 768, True)])
+def test_gemm_fused_layernorm_pooled(lib, pair, clips, rows, K, want_y):
+    """Mean-pooling over the token rows of every clip as a by-product of the fc2 / out_proj epilogue: pooled_raw = mean of the raw
+    Linear output (a mean-aggregated hook), pooled_y = mean of the LayerNorm output; clips of `rows` rows straddle the 32-row boxes
+    and the 128 / 256-row tiles.  Fixed-point accumulation: two runs are bit-identical."""
+    N, alpha, M = 768, 2.2133638, clips * rows
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g) + 0.3
+    gamma = torch.randn(N, device="cuda", generator=g)
+    beta = torch.randn(N, device="cuda", generator=g)
+    lin = A.float() @ W.float().T + bias
+    ref = torch.nn.functional.layer_norm(lin + alpha * res, (N,), gamma, beta, 1e-5)
+    nbytes = lib.avexk_gemm_ln_scratch_bytes(M)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    pool_ws = torch.empty(2 * clips * N * 8, dtype=torch.uint8, device="cuda")
+    outs = []
+    for rep in range(2):
+        p_raw = torch.full((clips, N), float("nan"), device="cuda")
+        p_y = torch.full((clips, N), float("nan"), device="cuda") if want_y else None
+        o32 = torch.full((M, N), float("nan"), device="cuda") if rep == 0 else None  # second run: pooled outputs only
+        _check(lib.avexk_gemm_bf16_ln_pooled(A.data_ptr(), K, W.data_ptr(), K, M, N, K, bias.data_ptr(), None, res.data_ptr(), alpha,
+                                             gamma.data_ptr(), beta.data_ptr(), 1e-5, o32.data_ptr() if o32 is not None else None, None,
+                                             scratch.data_ptr(), nbytes, rows, p_raw.data_ptr(), p_y.data_ptr() if want_y else None,
+                                             pool_ws.data_ptr(), _stream()), lib)  # fmt: skip
+        outs.append((p_raw, p_y))
+        if o32 is not None:
+            assert (o32 - ref).abs().max().item() <= 3e-3
+    p_raw, p_y = outs[0]
+    assert (p_raw - lin.view(clips, rows, N).mean(1)).abs().max().item() <= 5e-4
+    if want_y:
+        assert (p_y - ref.view(clips, rows, N).mean(1)).abs().max().item() <= 5e-4
+        assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])
+    # fewer than 32 rows per clip cannot be pooled in the epilogue: loud refusal
+    assert lib.avexk_gemm_bf16_ln_pooled(A.data_ptr(), K, W.data_ptr(), K, 16, N, K, bias.data_ptr(), None, res.data_ptr(), alpha,
+                                         gamma.data_ptr(), beta.data_ptr(), 1e-5, None, None, scratch.data_ptr(), nbytes, 16,
+                                         p_raw.data_ptr(), None, pool_ws.data_ptr(), _stream()) != 0  # fmt: skip
+
+
 def test_gemm_rejects_bad_shapes(lib):
     A = torch.zeros(8, 100, device="cuda", dtype=torch.bfloat16)
     assert lib.avexk_gemm_bf16(A.data_ptr(), 100, A.data_ptr(), 100, 8, 16, 100, None, 0, None, None, 0.0, A.data_ptr(), 16, 1, _stream()) != 0

@@ -75,14 +75,14 @@ def test_melspec_unnormalised_and_minmax():
                                             (300, 40, 240, 0, False), (64 * 5, 1280, 320, 1, False), (129, 112, 672, 0, True)])
 def test_conv1x1(lib, M, N, K, silu, res):
     g = torch.Generator(device="cuda").manual_seed(M + N)
-    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
-    W = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).to(torch.bfloat16)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.float16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).to(torch.float16)
     scale = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
     shift = 0.3 * torch.randn(N, device="cuda", generator=g)
-    R = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16) if res else None
+    R = torch.randn(M, N, device="cuda", generator=g).to(torch.float16) if res else None
     raw = torch.empty(M, N, device="cuda")
-    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    _check(lib.avexk_conv1x1_bf16(A.data_ptr(), W.data_ptr(), M, N, K, scale.data_ptr(), shift.data_ptr(), silu,
+    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    _check(lib.avexk_conv1x1_f16(A.data_ptr(), W.data_ptr(), M, N, K, scale.data_ptr(), shift.data_ptr(), silu,
                                   R.data_ptr() if res else None, raw.data_ptr(), out.data_ptr(), 1, _stream()), lib)  # fmt: skip
     acc = A.float() @ W.float().T
     ref = acc * scale + shift
@@ -91,20 +91,20 @@ def test_conv1x1(lib, M, N, K, silu, res):
     if res:
         ref = ref + R.float()
     assert (raw - acc).abs().max().item() <= 1e-4 * max(1.0, acc.abs().max().item())
-    assert (out.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())  # bf16 output rounding
+    assert (out.float() - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())  # fp16 output rounding
 
 
 @pytest.mark.parametrize("B,H,W,C,k,stride", [(2, 64, 51, 32, 3, 1), (1, 64, 101, 96, 3, 2), (3, 32, 26, 144, 5, 2),
                                               (2, 8, 7, 480, 5, 1), (2, 4, 4, 1152, 3, 1), (1, 9, 13, 240, 3, 2)])
 def test_dwconv(lib, B, H, W, C, k, stride):
     g = torch.Generator(device="cuda").manual_seed(C + k)
-    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.float16)
     w = torch.randn(C, 1, k, k, device="cuda", generator=g) / k
     scale = 1.0 + 0.2 * torch.randn(C, device="cuda", generator=g)
     shift = 0.3 * torch.randn(C, device="cuda", generator=g)
     p = (k - 1) // 2
     Ho, Wo = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
-    out = torch.empty(B, Ho, Wo, C, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(B, Ho, Wo, C, device="cuda", dtype=torch.float16)
     se = torch.empty(B, C, device="cuda")
     ws = torch.empty(2 * B * C + C * k * k, device="cuda")
     _check(lib.avexk_dwconv_nhwc(x.data_ptr(), B, H, W, C, k, stride, w.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -113,7 +113,7 @@ def test_dwconv(lib, B, H, W, C, k, stride):
     ref = torch.nn.functional.silu(ref * scale[None, :, None, None] + shift[None, :, None, None])
     got = out.float().permute(0, 3, 1, 2)
     assert got.shape == ref.shape
-    assert (got - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
     ref_se = ref.sum(dim=(2, 3))
     assert (se - ref_se).abs().max().item() <= 1e-3 * max(1.0, ref_se.abs().max().item())
 
@@ -164,15 +164,15 @@ def test_effnet_forward_and_hooks_vs_reference(case):
     for n, c, e, m in report:
         print(f"  {n:36s} cos {c:.5f}  max|err| {e:.3e}  (|ref| max {m:.2f})")
     print(f"  features cos {fcos:.5f}; aggregated-mean embedding cos {acos:.5f}")
-    # stem hook: fp32 math on the normalised image -> tight; deeper layers: bf16 activations through a random-init,
-    # BN-calibrated network that amplifies perturbations (the reference under bf16 autocast scores
-    # 0.958 against itself in fp32 at the head); gates sit well above that yardstick
+    # stem hook: fp32 math on the normalised image -> tight.  Every deeper layer, the features and the aggregated embedding:
+    # north_star's per-layer cosine >= 0.999.  The network is random-init and BN-calibrated, i.e. it amplifies perturbations
+    # (the reference itself under bf16 autocast scores 0.958 against its own fp32 run at the head; this
+    # path with bf16 storage reached 0.997 / 0.98) -- fp16 storage and operands are what meet the gate, end to end, without
+    # a separate fp32 mode.
     assert report[0][1] >= 0.99999 and report[0][2] <= 1e-3
-    for n, c, e, m in report[1:8]:
+    for n, c, e, m in report[1:]:
         assert c >= 0.999, (n, c)
-    for n, c, e, m in report[8:]:
-        assert c >= 0.99, (n, c)
-    assert fcos >= 0.98 and acos >= 0.995
+    assert fcos >= 0.999 and acos >= 0.999
 
 
 def test_effnet_vs_oracle_same_rounding_free_path():
@@ -185,7 +185,7 @@ def test_effnet_vs_oracle_same_rounding_free_path():
     ora = OEF.forward(W, img)
     c = _cos(feats, ora["features"])
     print(f"features vs oracle: cos {c:.5f}, shape {feats.shape}")
-    assert feats.shape == ora["features"].shape and c >= 0.98
+    assert feats.shape == ora["features"].shape and c >= 0.999
 
 
 def test_effnet_logits_vs_reference():
@@ -196,7 +196,7 @@ def test_effnet_logits_vs_reference():
     assert logits.shape == z["logits"].shape
     c = _cos(logits, z["logits"])
     print(f"logits cos {c:.5f} max|err| {np.abs(logits - z['logits']).max():.3e} (|ref| max {np.abs(z['logits']).max():.2f})")
-    assert c >= 0.995
+    assert c >= 0.999
 
 
 def test_effnet_errors():

@@ -121,3 +121,43 @@ def test_model_copies_and_pickles_without_native_handles():
     assert f._handle is None and torch.equal(f.window, m.fbank.window)
     assert m.__getstate__()["_engine"] is None
     m._engine, m.fbank._handle = None, None  # nothing real to destroy
+
+
+def test_checkpoint_key_handling_and_streamed_safetensors(tmp_path):
+    """checkpoints load with the reference's key rules (utils/utils.py:509-570, load.py:521-570) -- `module.` / `model.`
+    prefixes, head layers dropped in features-only mode, `backbone.` added or removed to fit -- and a .safetensors file is streamed
+    tensor by tensor into the parameters (same result as reading it whole)."""
+    from safetensors.torch import save_file
+
+    from avex_b200 import plugin
+    from avex_b200.plugin import beats_model  # noqa: F401
+    from avex_b200.plugin.load import _resolve_keys
+
+    target = ["backbone.post_extract_proj.weight", "backbone.encoder.layers.0.fc1.weight", "classifier.weight"]
+    got = _resolve_keys(["module.post_extract_proj.weight", "model.encoder.layers.0.fc1.weight", "classifier.weight", "head.bias"],
+                        target, keep_classifier=False)
+    assert got == {"module.post_extract_proj.weight": "backbone.post_extract_proj.weight",
+                   "model.encoder.layers.0.fc1.weight": "backbone.encoder.layers.0.fc1.weight"}
+    # a target whose own keys start with `model.` (EfficientNet wrapper) keeps that prefix
+    assert _resolve_keys(["model.features.0.0.weight"], ["model.features.0.0.weight"], True) == {"model.features.0.0.weight": "model.features.0.0.weight"}
+    assert _resolve_keys(["backbone.x.weight"], ["x.weight"], True) == {"backbone.x.weight": "x.weight"}
+
+    spec = plugin.ModelSpec(name="beats", device="cpu", init_config=dict(encoder_layers=1, finetuned_model=True))
+    plugin.register_model("cpu_ckpt_test", spec)
+    torch.manual_seed(3)
+    src = plugin.load_model("cpu_ckpt_test", device="cpu", return_features_only=True)
+    sd = {("module." + k[len("backbone."):]): v.detach().clone().contiguous() for k, v in src.state_dict().items()
+          if "relative_attention_bias" not in k or ".layers.0." in k}  # DDP-style names, no `backbone.` prefix
+    sd["module.classifier.weight"] = torch.zeros(3, 768)  # must be dropped in features-only mode
+    path = str(tmp_path / "ckpt.safetensors")
+    save_file(sd, path)
+    torch.manual_seed(4)
+    dst = plugin.load_model("cpu_ckpt_test", device="cpu", checkpoint_path=path, return_features_only=True)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    pt = str(tmp_path / "ckpt.pt")
+    torch.save({"model_state_dict": sd}, pt)
+    torch.manual_seed(5)
+    dst2 = plugin.load_model("cpu_ckpt_test", device="cpu", checkpoint_path=pt, return_features_only=True)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst2.state_dict()[k], v), k
