@@ -67,6 +67,7 @@ static_assert(SMEM_BYTES <= 232448, "attention_tc: shared memory budget");
 
 struct AttnTcArgs {
   int B, N, H;
+  uint32_t m_pairs, m_heads;  // reciprocals for fast_div by ceil(N / 256) and H
   int n_items;             // B * H * ceil(N / 256): read from the constant bank where needed (a register-resident copy spilled)
   const float* gate;       // [B*N, H]: gate_a * (gate_b * grep_a - 1) + 2 of every (token, head) (backbone.py:544-550)
   const float* bias_vec;   // [H, 2N-1]
@@ -259,11 +260,19 @@ struct Item {
   int b, h, q0;
   bool has_b;  // the pair's second tile holds at least one valid query row
 };
-__device__ __forceinline__ Item decode_item(int item, int npairs, int H, int N) {
+// n / d through a host-computed reciprocal (magic = floor(2^32 / d) + 1, exact for n * d < 2^32): five instructions instead of
+// the ~25 of a runtime integer division, which the softmax warps ended up repeating inside their tile loop
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t magic) {
+  if (d == 1) return n;  // the reciprocal of 1 does not fit 32 bits
+  uint32_t q = __umulhi(n, magic);
+  if (q * d > n) --q;  // (magic rounds up: the quotient can be one too large)
+  return q;
+}
+__device__ __forceinline__ Item decode_item(int item, int npairs, int H, int N, uint32_t m_pairs, uint32_t m_heads) {
   Item it;
-  const int pair = item % npairs, bh = item / npairs;
-  it.h = bh % H;
-  it.b = bh / H;
+  const uint32_t bh = fast_div(item, npairs, m_pairs), pair = item - bh * npairs;
+  it.b = fast_div(bh, H, m_heads);
+  it.h = bh - it.b * H;
   it.q0 = pair * 2 * BQ;
   it.has_b = it.q0 + BQ < N;
   return it;
@@ -333,7 +342,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const Item it = decode_item(item, npairs, a.H, N);
+        const Item it = decode_item(item, npairs, a.H, N, a.m_pairs, a.m_heads);
         const int col_k = (a.H + it.h) * HD, col_v = (2 * a.H + it.h) * HD;
         for (int t = 0; t < n_kv; ++t) {
           ptx::mbar_wait(&kv_empty[stage], phase ^ 1);
@@ -348,7 +357,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       // ===================== Q loader =====================
       uint32_t cnt[2] = {0, 0};
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const Item it = decode_item(item, npairs, a.H, N);
+        const Item it = decode_item(item, npairs, a.H, N, a.m_pairs, a.m_heads);
         for (int g = 0; g < 2; ++g) {
           if (g == 1 && !it.has_b) break;
           ptx::mbar_wait(&q_empty[g], (cnt[g] & 1) ^ 1);
@@ -392,8 +401,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       const int n_ord = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // items of this CTA
       auto has_group = [&](int g, int k) -> bool {  // group 1 only exists when the pair's second tile holds a valid query row
         if (g == 0) return true;
-        const int item = blockIdx.x + k * gridDim.x;
-        return (item % npairs) * 2 * BQ + BQ < N;
+        const uint32_t item = blockIdx.x + k * gridDim.x;
+        return (int)(item - fast_div(item, npairs, a.m_pairs) * npairs) * 2 * BQ + BQ < N;
       };
       // positions are packed (item ordinal << 8 | tile): one register each, and "is ahead of" is an integer compare
       uint32_t ps[2] = {0, 0};  // next S_g
@@ -504,8 +513,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     bool tile_dead = false;  // the tile about to be processed holds a PADDED key (group-uniform): masked path
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const Item it = decode_item(item, npairs, a.H, N);
+      Item it = decode_item(item, npairs, a.H, N, a.m_pairs, a.m_heads);
       if (g == 1 && !it.has_b) continue;
+      // pin the decoded fields: under register pressure the compiler otherwise re-derives them (two integer divisions, ~60
+      // instructions) at every use inside the tile loop
+      asm volatile("" : "+r"(it.b), "+r"(it.h), "+r"(it.q0));
       const int q0 = it.q0 + g * BQ, b = it.b, h = it.h;
       if (!have_tab) {
         const int dead0 = fetch_dead(it, 0);
@@ -547,7 +559,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           nbias = fetch_bias(it, t + 1);
           ndead = fetch_dead(it, t + 1);
         } else if (item + (int)gridDim.x < n_items) {  // decoded here, not held in registers across the tiles
-          const Item nit = decode_item(item + gridDim.x, npairs, a.H, N);
+          const Item nit = decode_item(item + gridDim.x, npairs, a.H, N, a.m_pairs, a.m_heads);
           if (!(g == 1 && !nit.has_b)) {
             nbias = fetch_bias(nit, 0);
             ndead = fetch_dead(nit, 0);
@@ -733,7 +745,10 @@ int attention_launch(const void* qkv, int B, int N, int H, const float* gate, co
   if (rc) return rc;
   const long long items = (long long)B * H * ceil_div(N, 2 * BQ);
   AVEXK_CHECK_ARG(items < (1LL << 31), "attention: too many work items");
-  AttnTcArgs a{B, N, H, (int)items, gate, bias_vec, key_pad, reinterpret_cast<__nv_bfloat16*>(out)};
+  const uint32_t npairs = (uint32_t)ceil_div(N, 2 * BQ);
+  AVEXK_CHECK_ARG(items * (long long)(npairs > (uint32_t)H ? npairs : (uint32_t)H) < (1LL << 32), "attention: too many work items for the reciprocal decode");
+  AttnTcArgs a{B, N, H, (uint32_t)(0x100000000ULL / npairs) + 1u, (uint32_t)(0x100000000ULL / (uint32_t)H) + 1u, (int)items, gate, bias_vec, key_pad,
+               reinterpret_cast<__nv_bfloat16*>(out)};
   const int grid = (int)(items < num_sms() ? items : num_sms());
   prof_begin(st, KID_ATTN, 4.0 * B * H * (double)N * N * HD);
   attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(map, map_out, a);

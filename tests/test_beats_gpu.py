@@ -105,7 +105,8 @@ def test_pooled_hooks_are_formed_on_device():
         got = model.extract_embeddings(wav, padding_mask=m, aggregation="mean")
         assert got.shape == (2, 3 * 768)
         assert (got - want).abs().max().item() <= 2e-5, (got - want).abs().max().item()
-        assert torch.cuda.max_memory_allocated() == before  # no [B,N,768] hook tensors were allocated
+        # no [B,N,768] hook tensors were allocated (3 layers x 2 x 96 x 768 fp32 = 1.7 MB would show; the pooled outputs are 18 KB)
+        assert torch.cuda.max_memory_allocated() - before < 256 * 1024
     res = model.backbone.run(wav, None, want_features=False, hook_layers=[0, 1, 2], hook_pool=True)
     assert all(t.shape == (2, 768) for t in res["hooks"].values())
     seen = []
