@@ -288,8 +288,12 @@ extern "C" int avexk_beats_forward(avexk_beats_t* h, const float* wav, int B, in
     if (fuse_ln && (fuse_level >= 2 || K > C)) {
       const int zero = ln_first;
       ln_first = 0;
-      return gemm_bf16_ln_launch(A, K, W, K, (int)M, K, bias, raw, x, alpha, gamma, beta, d.ln_eps, dst_f32, dst_bf16, ln_ws, ln_ws_bytes,
-                                 zero, st, pool_raw, pool_y, N);
+      const int r = gemm_bf16_ln_launch(A, K, W, K, (int)M, K, bias, raw, x, alpha, gamma, beta, d.ln_eps, dst_f32, dst_bf16, ln_ws, ln_ws_bytes,
+                                        zero, st, pool_raw, pool_y, N);
+      // AVEXK_ENOMEM: the grid of the fused epilogue cannot be co-resident on this device partition -> separate launches below
+      // (only possible without fused pooling, which the caller requests only when it has checked the same condition)
+      if (r != AVEXK_ENOMEM || pool_raw != nullptr || pool_y != nullptr) return r;
+      if (dst_f32 == nullptr) dst_f32 = x;
     }
     int r = gemm_bf16_launch(A, K, W, K, (int)M, C, K, bias, 0, raw, x, alpha, tmp, C, 0, st);
     if (r) return r;

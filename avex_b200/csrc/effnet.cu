@@ -19,6 +19,8 @@
 //     shared-memory atomics -> one global atomic per (CTA, channel));
 //   * SE: a tiny per-clip MLP kernel, then the channel scale applied in place.
 // Roofline: HBM (about 29 FLOP/B overall); the pointwise GEMMs are reported against the tensor pipe.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -138,7 +140,6 @@ stem_kernel(const float* __restrict__ mel, const unsigned* __restrict__ minmax, 
 // depthwise k x k conv + BN + SiLU, NHWC bf16, with the squeeze-excitation sums
 // ---------------------------------------------------------------------------------------------------------
 constexpr int DW_TW = 4;        // consecutive output pixels (along W) per thread
-constexpr int DW_QUADS = 64;    // pixel quads per CTA (256 output pixels)
 constexpr float SE_FIX = 16777216.0f;  // 2^24
 // One thread = 8 channels x DW_TW consecutive output pixels of one row.  Per kernel row it loads the (DW_TW-1)*S + K input
 // columns once (16-byte loads, channels-last) and the K weight vectors once, and reuses both across the DW_TW outputs:
@@ -147,7 +148,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(256)
 dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho, int Wo,
               const float* __restrict__ wkk, const float* __restrict__ scale, const float* __restrict__ shift,
-              __nv_bfloat16* __restrict__ out, unsigned long long* __restrict__ se_sum) {
+              __nv_bfloat16* __restrict__ out, unsigned long long* __restrict__ se_sum, int quads_per_cta) {
   // squeeze-excitation sums in 40.24 fixed point: integer adds are associative, so the atomics below give the same bits
   // whatever order the pixel groups / CTAs arrive in (a float atomicAdd made results differ from run to run)
   extern __shared__ unsigned long long sse[];  // [C]
@@ -158,7 +159,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho,
   __syncthreads();
   constexpr int PAD = (K - 1) / 2, NC = (DW_TW - 1) * S + K;
   const int quads_per_row = (Wo + DW_TW - 1) / DW_TW, nquads = Ho * quads_per_row;
-  const int q_end = min(nquads, (int)(blockIdx.x + 1) * DW_QUADS);
+  const int q_end = min(nquads, (int)(blockIdx.x + 1) * quads_per_cta);
   float se[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) se[i] = 0.f;
@@ -166,7 +167,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho,
     const float4 sc0 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8)), sc1 = __ldg(reinterpret_cast<const float4*>(scale + cv * 8 + 4));
     const float4 sh0 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8)), sh1 = __ldg(reinterpret_cast<const float4*>(shift + cv * 8 + 4));
     const __nv_bfloat16* src = in + (size_t)b * H * W * C + cv * 8;
-    for (int q = blockIdx.x * DW_QUADS + qg; q < q_end; q += QG) {
+    for (int q = blockIdx.x * quads_per_cta + qg; q < q_end; q += QG) {
       const int ho = q / quads_per_row, wo0 = (q - ho * quads_per_row) * DW_TW;
       float acc[DW_TW][8];
 #pragma unroll
@@ -367,12 +368,18 @@ int launch_dwconv(const __nv_bfloat16* in, int B, int H, int W, int C, int k, in
   if (B == 0) return AVEXK_OK;
   const int Ho = conv_out(H, k, stride), Wo = conv_out(W, k, stride);
   const int nquads = Ho * ceil_div(Wo, DW_TW);
-  dim3 grid(ceil_div(nquads, DW_QUADS), B);
+  // pixel quads per CTA: enough work per CTA to amortise its fixed cost (zeroing / flushing the squeeze-excitation sums, two
+  // barriers), few enough CTAs-worth to keep every SM busy.  AVEXK_DW_QUADS overrides (measurement).
+  static const int quads_env = [] { const char* e = getenv("AVEXK_DW_QUADS"); return e ? atoi(e) : 0; }();
+  int qpc = quads_env > 0 ? quads_env : 256;
+  const int in_flight = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  if (qpc < in_flight) qpc = in_flight;
+  dim3 grid(ceil_div(nquads, qpc), B);
   const size_t sm = C * sizeof(unsigned long long);
-  if (k == 3 && stride == 1) dwconv_kernel<3, 1><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum);
-  else if (k == 3) dwconv_kernel<3, 2><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum);
-  else if (stride == 1) dwconv_kernel<5, 1><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum);
-  else dwconv_kernel<5, 2><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum);
+  if (k == 3 && stride == 1) dwconv_kernel<3, 1><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum, qpc);
+  else if (k == 3) dwconv_kernel<3, 2><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum, qpc);
+  else if (stride == 1) dwconv_kernel<5, 1><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum, qpc);
+  else dwconv_kernel<5, 2><<<grid, 256, sm, st>>>(in, H, W, C, Ho, Wo, wkk, scale, shift, out, se_sum, qpc);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
 }

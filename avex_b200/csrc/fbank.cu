@@ -177,39 +177,63 @@ fbank_kernel(const float* __restrict__ wav, long long stride, int T, int F, int 
 
   const bool vec_ok = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(wav) & 15) == 0);
 
+  // Staging loads: all 12 float4 (+ the warp-edge samples) of a chunk are issued before the first one is consumed, ahead of the
+  // CTA barrier (with one dependent load per loop iteration the staging pass took half of all stall samples; holding the next
+  // chunk's loads across the mel phase instead spilled).
+  constexpr int NIT = (NQ + THREADS - 1) / THREADS;
+  float4 A[NIT], Bv[NIT];
+  float ea[NIT], eb[NIT];  // previous sample at the warp edge (lane 0 only)
+  auto prefetch = [&](int item) {
+    const int b = item / chunks, c = item - b * chunks;
+    const long long s0 = (long long)c * FPC * HOP;
+    const float* src = wav + (long long)b * stride;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+      const int u = k * THREADS + tid;
+      const bool act = u < NQ;
+      const long long sa = s0 + 4 * u, sb = sa + HOP;
+      A[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      Bv[k] = A[k];
+      ea[k] = eb[k] = 0.f;
+      if (act) {
+        if (vec_ok && sb + 3 < T) {
+          A[k] = __ldg(reinterpret_cast<const float4*>(src + sa));
+          Bv[k] = __ldg(reinterpret_cast<const float4*>(src + sb));
+        } else {
+          auto ld = [&](long long s) { return s < T ? __ldg(src + s) : 0.f; };
+          A[k] = make_float4(ld(sa), ld(sa + 1), ld(sa + 2), ld(sa + 3));
+          Bv[k] = make_float4(ld(sb), ld(sb + 1), ld(sb + 2), ld(sb + 3));
+        }
+        if (lane == 0) {
+          ea[k] = sa > 0 && sa - 1 < T ? __ldg(src + sa - 1) : 0.f;
+          eb[k] = sb - 1 < T ? __ldg(src + sb - 1) : 0.f;
+        }
+      }
+    }
+  };
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int b = item / chunks, c = item - b * chunks;
     const int f0 = c * FPC;
     const long long s0 = (long long)f0 * HOP;
     const float* src = wav + (long long)b * stride;
+    prefetch(item);   // issued ahead of the barrier: in flight while the slowest warp of the CTA finishes the previous chunk
     __syncthreads();  // the previous chunk's readers of sD / sPS / sX0 are done (and the tables are in place)
 
     // ---- staging: d[i] = x[i] - 0.97 x[i-1] once per sample, stored as (d[i], d[i+160]); partial sums for the means --------
-#pragma unroll 1
-    for (int u0 = 0; u0 < NQ; u0 += THREADS) {  // uniform trip count: the shuffles below need the whole warp
-      const int u = u0 + tid;
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {  // uniform trip count: the shuffles below need the whole warp
+      const int u = k * THREADS + tid;
       const bool act = u < NQ;
-      const long long sa = s0 + 4 * u, sb = sa + HOP;
-      float4 A = make_float4(0.f, 0.f, 0.f, 0.f), Bv = A;
-      if (act) {
-        if (vec_ok && sb + 3 < T) {
-          A = __ldg(reinterpret_cast<const float4*>(src + sa));
-          Bv = __ldg(reinterpret_cast<const float4*>(src + sb));
-        } else {
-          auto ld = [&](long long s) { return s < T ? __ldg(src + s) : 0.f; };
-          A = make_float4(ld(sa), ld(sa + 1), ld(sa + 2), ld(sa + 3));
-          Bv = make_float4(ld(sb), ld(sb + 1), ld(sb + 2), ld(sb + 3));
-        }
-      }
+      const long long sa = s0 + 4 * u;
       // previous sample: the neighbour lane's .w, except at the warp edge (and the clip start: replicate, beats.py:143)
-      float pa = __shfl_up_sync(0xffffffffu, A.w, 1);
-      float pb = __shfl_up_sync(0xffffffffu, Bv.w, 1);
-      if (lane == 0 && act) {
-        pa = sa > 0 ? (sa - 1 < T ? __ldg(src + sa - 1) : 0.f) : A.x;
-        pb = sb - 1 < T ? __ldg(src + sb - 1) : 0.f;
+      float pa = __shfl_up_sync(0xffffffffu, A[k].w, 1);
+      float pb = __shfl_up_sync(0xffffffffu, Bv[k].w, 1);
+      if (lane == 0) {
+        pa = sa > 0 ? ea[k] : A[k].x;
+        pb = eb[k];
       }
       if (act) {
-        const P2 x0 = make_float2(A.x, Bv.x), x1 = make_float2(A.y, Bv.y), x2 = make_float2(A.z, Bv.z), x3 = make_float2(A.w, Bv.w);
+        const P2 x0 = make_float2(A[k].x, Bv[k].x), x1 = make_float2(A[k].y, Bv[k].y), x2 = make_float2(A[k].z, Bv[k].z), x3 = make_float2(A[k].w, Bv[k].w);
         const P2 d0 = pfmas(make_float2(pa, pb), -0.97f, x0), d1 = pfmas(x0, -0.97f, x1);  // beats.py:144
         const P2 d2 = pfmas(x1, -0.97f, x2), d3 = pfmas(x2, -0.97f, x3);
         // 16-byte unit e (two entries) lives at e ^ ((e >> 3) & 1): the eight lanes of a store phase write units 2u (then 2u+1)

@@ -857,25 +857,42 @@ int launch_mode(const void* A, long long lda, const void* W, long long ldw, cons
   const int m_units = ceil_div(g.M, C::UM), n_blocks = ceil_div(g.N, BN);
   const int work = m_units * n_blocks;
   const int max_units = PAIR ? num_sms() / 2 : num_sms();
-  const int units = work < max_units ? work : max_units;
-  prof_begin(st, KID_GEMM, 2.0 * g.M * g.N * g.K);
-  if (PAIR) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * units);
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, ma, mb, mres, my, mxb, g));
-  } else {
-    gemm_bf16_kernel<MODE, PAIR, EW, DEEPK><<<units, NTHREADS, C::SMEM_BYTES, st>>>(ma, mb, mres, my, mxb, g);
+  int units = work < max_units ? work : max_units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // The persistent grid must be CO-RESIDENT: the fused LayerNorm epilogue spins on counters that CTAs of the same row block
+  // publish, so an unscheduled peer would never arrive.  Ask the runtime how many clusters of this configuration fit (MPS
+  // thread limits, green contexts or a concurrent kernel can shrink it below #SMs) and size the grid to that; if not even the
+  // LN_NB tiles of one row block fit, refuse -- the caller falls back to the unfused GEMM + LayerNorm launches.
+  {
+    static int resident[64] = {};
+    if (resident[dev_] == 0) {
+      int ncl = 0;
+      cfg.gridDim = dim3(PAIR ? 2 * max_units : max_units);
+      if (cudaOccupancyMaxActiveClusters(&ncl, gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, &cfg) != cudaSuccess || ncl <= 0) {
+        cudaGetLastError();
+        ncl = -1;  // cannot be queried: keep the #SM-based grid
+      }
+      resident[dev_] = ncl;
+    }
+    if (resident[dev_] > 0 && units > resident[dev_]) units = resident[dev_];
+    if (MODE == MODE_RES && g.ln_gamma != nullptr && units < LN_NB && work >= LN_NB) {
+      set_error("gemm+LN: only %d co-resident tile units (need %d): fused LayerNorm epilogue unavailable", units, LN_NB);
+      return AVEXK_ENOMEM;
+    }
   }
+  cfg.gridDim = dim3(PAIR ? 2 * units : units);
+  prof_begin(st, KID_GEMM, 2.0 * g.M * g.N * g.K);
+  AVEXK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<MODE, PAIR, EW, DEEPK>, ma, mb, mres, my, mxb, g));
   prof_end(st);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
