@@ -117,6 +117,24 @@ def test_pooled_hooks_are_formed_on_device():
     assert (got2 - got).abs().max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("seconds,precision", [(0.5, "bf16"), (1.0, "fp32"), (0.5, "fp32")])
+def test_pooled_hooks_fallback_paths(seconds, precision):
+    """The epilogue pooling needs >= 32 tokens per clip and the bf16 engine; shorter clips (0.5 s -> N = 24) and the fp32 mode go
+    through the materialise-then-pool path -- same numbers either way."""
+    model, _ = _build(2, 7)
+    model.backbone.precision = precision
+    g = torch.Generator(device="cuda").manual_seed(int(seconds * 10))
+    wav = torch.randn(3, int(16000 * seconds), device="cuda", generator=g) * 0.1
+    model.register_hooks_for_layers(["all"])
+    full = model.extract_embeddings(wav, aggregation="none")
+    want = torch.cat([h.mean(dim=1) for h in full], dim=1)
+    got = model.extract_embeddings(wav, aggregation="mean")
+    assert got.shape == (3, 3 * 768) and torch.isfinite(got).all()
+    assert (got - want).abs().max().item() <= 2e-5
+    res = model.backbone.run(wav, None, want_features=True, want_pooled=True)
+    assert (res["pooled"] - res["features"].mean(dim=1)).abs().max().item() <= 2e-5
+
+
 def test_classifier_mode_masked_mean_pool():
     case = cases.beats_cases()["L2_2x2s_mask"]
     from avex_b200 import plugin
