@@ -260,3 +260,19 @@ def test_long_clip_equals_short_clip_under_padding_mask():
     assert f_short.shape == (2, 496, 768) and f_long.shape == (2, 2992, 768)
     assert torch.isfinite(f_long).all()
     _cmp("60 s masked vs 10 s", f_long[:, :496].cpu().numpy(), f_short.cpu().numpy())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """the dynamic-shared-memory opt-in is a per-DEVICE function attribute -- a model on cuda:1 after one on cuda:0 in
+    the same process must launch (the flags were once per process)."""
+    model0, _ = _build(2, 1)
+    wav = torch.randn(2, 16000, generator=torch.Generator().manual_seed(3)) * 0.1
+    with torch.no_grad():
+        f0 = model0(wav.cuda(0))
+    import copy
+
+    model1 = copy.deepcopy(model0).to("cuda:1")
+    with torch.cuda.device(1), torch.no_grad():
+        f1 = model1(wav.cuda(1))
+    assert torch.equal(f0.cpu(), f1.cpu())
