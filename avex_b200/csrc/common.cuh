@@ -90,8 +90,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // fp16 storage of bounded activations (EfficientNet path, pos-conv operands): three more mantissa bits than bf16 at the same
 // tensor-core rate; values beyond the fp16 range saturate instead of becoming inf
 __device__ __forceinline__ uint32_t pack_h16(float lo, float hi) {
-  const __half2 t = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
-  return *reinterpret_cast<const uint32_t*>(&t);
+  uint32_t r;  // one F2FP.SATFINITE: |x| > 65504 -> +-65504, NaN stays NaN
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ float2 unpack_h16(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 

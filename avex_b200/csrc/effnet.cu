@@ -25,6 +25,8 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
 
 struct avexk_effnet {
   std::vector<avexk_effnet_block_cfg> cfg;
@@ -230,6 +232,237 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// depthwise conv, sliding-window form fed by TMA (the production kernel)
+// ---------------------------------------------------------------------------------------------------------
+// A persistent CTA works through tiles of (clip, band of output rows, G*DW_TW output columns, CSL channels).  One producer
+// thread streams the tile's INPUT rows through a shared-memory ring with 4-D TMA boxes [1, 1, ncw columns, CSL channels]; the
+// map's out-of-bounds zero fill is the convolution's zero padding, so the arithmetic has no edge predicates, and the ring
+// keeps several rows (tens of KB per CTA) in flight without holding a register.  A consumer thread owns CH channels x DW_TW
+// output columns and walks DOWN the band: the K*K weights of its channels stay in registers, every input row is read once
+// (NC = (DW_TW-1)*S + K columns from shared memory, conflict-free: lanes = consecutive channels) and scattered into the
+// ceil(K/S) output rows it contributes to, whose accumulators rotate through a register window (the row loop is unrolled
+// over one period of that rotation, so every slot index is a compile-time constant).  Two channels ride in one packed fp32x2
+// FMA.  Against the per-output-row kernel above: K (stride 1) or K/2 (stride 2) times fewer loads per output, no weight
+// traffic, no address arithmetic in the row loop -- the layers become DRAM / FMA-issue bound instead of LSU bound.
+// silu for a channel pair: one packed multiply, two EX2, two RCP (no range fix-ups: ex2.approx.ftz saturates to +inf / 0, and
+// v * rcp(1 + inf) = -0 is the right limit)
+__device__ __forceinline__ float2 silu2(float2 v) {
+  const float2 q = __fmul2_rn(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  e = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+  return __fmul2_rn(v, r);
+}
+__host__ __device__ constexpr int pos_mod(int a, int m) { return ((a % m) + m) % m; }
+__host__ __device__ constexpr int floor_div(int a, int m) { return (a - pos_mod(a, m)) / m; }
+
+__device__ __forceinline__ void dw_lds(uint32_t addr, float2 (&x)[1]) {
+  uint32_t r;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
+  x[0] = unpack_h16(r);
+}
+__device__ __forceinline__ void dw_lds(uint32_t addr, float2 (&x)[2]) {
+  uint32_t r0, r1;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+  x[0] = unpack_h16(r0);
+  x[1] = unpack_h16(r1);
+}
+__device__ __forceinline__ void dw_store(__nv_bfloat16* p, const float2 (&y)[1]) { *reinterpret_cast<uint32_t*>(p) = pack_h16(y[0].x, y[0].y); }
+__device__ __forceinline__ void dw_store(__nv_bfloat16* p, const float2 (&y)[2]) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_h16(y[0].x, y[0].y), pack_h16(y[1].x, y[1].y));
+}
+
+constexpr int DW_MAX_RING = 8;
+struct DwTmaArgs {
+  int B, H, W, C, Ho, Wo;
+  int csl, pv, g;            // channels per tile, channel vectors (of CH) per column group, column groups per tile
+  int bh;                    // output rows per band
+  int n_cs, n_ct, n_band;    // tiles per clip: channel slices x column tiles x bands
+  int n_tiles, ring, slot_bytes, row_bytes, out_row_pitch;
+  const float *wkk, *scale, *shift;
+  __nv_bfloat16* out;
+  unsigned long long* se_sum;
+};
+struct DwTile {
+  int b, cs, ct, band;
+};
+__device__ __forceinline__ DwTile dw_decode(int tile, const DwTmaArgs& a) {  // channel slice slowest: a CTA rarely changes weights
+  DwTile t;
+  t.ct = tile % a.n_ct;
+  tile /= a.n_ct;
+  t.band = tile % a.n_band;
+  tile /= a.n_band;
+  t.b = tile % a.B;
+  t.cs = tile / a.B;
+  return t;
+}
+
+template <int K, int S, int CH>
+__global__ void __launch_bounds__(256, 2)
+dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a) {
+  constexpr int PAD = (K - 1) / 2, V = CH / 2, TW = DW_TW;
+  constexpr int NSLOT = (K + S - 1) / S;    // output rows with contributions in flight
+  constexpr int PERIOD = S * NSLOT;         // input rows after which the slot rotation repeats
+  constexpr int NC = (TW - 1) * S + K;      // input columns per consumer thread and row step
+  extern __shared__ unsigned char dw_smem_raw[];
+  unsigned char* smem = dw_smem_raw + ((128u - (ptx::smem_u32(dw_smem_raw) & 127u)) & 127u);
+  const uint32_t ring_a = ptx::smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.ring * a.slot_bytes);  // full[ring], empty[ring]
+  const uint32_t full_a = ptx::smem_u32(bars), empty_a = full_a + DW_MAX_RING * 8;
+  unsigned long long* sse = reinterpret_cast<unsigned long long*>(bars + 2 * DW_MAX_RING);  // [2][csl], 40.24 fixed point
+  const int n_cons_warps = blockDim.x / 32 - 1, n_cons = n_cons_warps * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&map_in);
+    for (int i = 0; i < a.ring; ++i) {
+      ptx::mbar_init(&bars[i], 1);
+      ptx::mbar_init(&bars[DW_MAX_RING + i], n_cons_warps);
+    }
+    ptx::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 2 * a.csl; i += blockDim.x) sse[i] = 0ull;
+  __syncthreads();
+
+  if (warp == n_cons_warps) {
+    // ===================== producer: one thread streams input rows of this CTA's tiles =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const DwTile t = dw_decode(tile, a);
+        const int ho0 = t.band * a.bh, rows = min(a.bh, a.Ho - ho0);
+        const int hi0 = ho0 * S - PAD, wi0 = t.ct * a.g * TW * S - PAD, nsteps = (rows - 1) * S + K;
+        for (int r = 0; r < nsteps; ++r) {
+          const int hi = hi0 + r;
+          if ((unsigned)hi >= (unsigned)a.H) continue;  // a padding row: the consumers know, nothing is sent
+          ptx::mbar_wait_a(empty_a + slot * 8, phase ^ 1);
+          ptx::mbar_arrive_expect_tx_a(full_a + slot * 8, a.row_bytes);
+          ptx::tma_load_4d_a(ring_a + slot * a.slot_bytes, &map_in, full_a + slot * 8, t.cs * a.csl, wi0, hi, t.b);
+          if (++slot == a.ring) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  const int tid = threadIdx.x;
+  const bool active = tid < a.pv * a.g;
+  const int cvv = active ? tid % a.pv : 0, cg = active ? tid / a.pv : 0;  // idle threads shadow thread 0 (no stores)
+  const uint32_t x_off = ((cg * TW * S) * a.csl + cvv * CH) * 2;          // this thread's first column inside a ring row
+  const uint32_t col_pitch = a.csl * 2;
+  int slot = 0, last_cs = -1, tile_par = 0;
+  uint32_t phase = 0;
+  float2 w[K * K][V], sh[V];  // BatchNorm folded: w = conv weight * scale, accumulators start from the shift
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, tile_par ^= 1) {
+    const DwTile t = dw_decode(tile, a);
+    const int c0 = t.cs * a.csl + cvv * CH;
+    if (t.cs != last_cs) {  // (CTA-uniform)
+      last_cs = t.cs;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float2 sc = __ldg(reinterpret_cast<const float2*>(a.scale + c0 + 2 * v));
+        sh[v] = __ldg(reinterpret_cast<const float2*>(a.shift + c0 + 2 * v));
+#pragma unroll
+        for (int kk = 0; kk < K * K; ++kk)
+          w[kk][v] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(a.wkk + (size_t)kk * a.C + c0 + 2 * v)), sc);
+      }
+    }
+    const int ho0 = t.band * a.bh, rows = min(a.bh, a.Ho - ho0), wo0 = (t.ct * a.g + cg) * TW;
+    const int hi0 = ho0 * S - PAD, r_last = (rows - 1) * S + K - 1;
+    const int nvalid = active ? a.Wo - wo0 : 0;  // output columns tt < nvalid are stored
+    __nv_bfloat16* dst = a.out + (((size_t)t.b * a.Ho + ho0) * a.Wo + wo0) * a.C + c0;  // advances one output row per emission
+    float2 se[V], acc[NSLOT][TW][V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) se[v] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s)
+#pragma unroll
+      for (int tt = 0; tt < TW; ++tt)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[s][tt][v] = sh[v];
+
+    for (int rb = 0; rb <= r_last; rb += PERIOD) {
+#pragma unroll
+      for (int u = 0; u < PERIOD; ++u) {
+        const int r = rb + u;
+        const bool row_in = (unsigned)(hi0 + r) < (unsigned)a.H && r <= r_last;  // tile-uniform
+        if (row_in) {
+          ptx::mbar_wait_a(full_a + slot * 8, phase);
+          const uint32_t xrow = ring_a + slot * a.slot_bytes + x_off;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            float2 x[V];
+            dw_lds(xrow + c * col_pitch, x);
+            if (c == NC - 1) {  // the row is in registers: hand the slot back to the producer
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_a(empty_a + slot * 8);
+            }
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+              if (pos_mod(u - ky, S) != 0) continue;  // this input row is not under tap row ky of any output row
+              const int s = pos_mod(floor_div(u - ky, S), NSLOT);
+#pragma unroll
+              for (int tt = 0; tt < TW; ++tt) {
+                const int kx = c - tt * S;
+                if (kx < 0 || kx >= K) continue;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                  if (ky == 0 && kx == 0) acc[s][tt][v] = __ffma2_rn(x[v], w[0][v], sh[v]);  // first tap (re)starts the slot
+                  else acc[s][tt][v] = __ffma2_rn(x[v], w[ky * K + kx][v], acc[s][tt][v]);
+                }
+              }
+            }
+          }
+          if (++slot == a.ring) { slot = 0; phase ^= 1; }
+        } else if (pos_mod(u, S) == 0) {  // a zero (padding) row under tap row 0: the slot still has to restart
+          const int s = pos_mod(floor_div(u, S), NSLOT);
+#pragma unroll
+          for (int tt = 0; tt < TW; ++tt)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[s][tt][v] = sh[v];
+        }
+        if (pos_mod(u - (K - 1), S) == 0) {  // tap row K-1 completes an output row
+          const int s = pos_mod(floor_div(u - (K - 1), S), NSLOT);
+          if (r >= K - 1 && r <= r_last) {
+#pragma unroll
+            for (int tt = 0; tt < TW; ++tt) {
+              if (tt >= nvalid) continue;
+              float2 y[V];
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                y[v] = silu2(acc[s][tt][v]);
+                se[v] = __fadd2_rn(se[v], y[v]);
+              }
+              dw_store(dst + tt * a.C, y);
+            }
+            dst += a.out_row_pitch;
+          }
+        }
+      }
+    }
+    if (a.se_sum != nullptr) {  // squeeze-excitation sums: registers -> shared (per tile) -> one global atomic per channel
+      unsigned long long* sb = sse + tile_par * a.csl;
+      if (active) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          atomicAdd(&sb[cvv * CH + 2 * v], static_cast<unsigned long long>(__float2ll_rn(se[v].x * SE_FIX)));
+          atomicAdd(&sb[cvv * CH + 2 * v + 1], static_cast<unsigned long long>(__float2ll_rn(se[v].y * SE_FIX)));
+        }
+      }
+      ptx::named_bar_sync(1, n_cons);
+      for (int i = tid; i < a.csl; i += n_cons) {
+        atomicAdd(a.se_sum + (size_t)t.b * a.C + t.cs * a.csl + i, sb[i]);
+        sb[i] = 0ull;  // this buffer is next written two tiles from now, behind the next tile's barrier
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // squeeze-excitation MLP per clip: s = sigmoid(W2 silu(W1 avg + b1) + b2)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -362,11 +595,96 @@ inline int conv_out(int n, int k, int stride) { return (n + 2 * ((k - 1) / 2) - 
 
 }  // namespace
 
+// Tile geometry of the TMA kernel for one layer: channels per tile (a divisor of C, multiple of 8), column groups per tile,
+// band height, ring depth.  Scored by (useful input columns / loaded columns) x (busy threads / launched consumer threads).
+struct DwPlan {
+  int csl = 0, pv = 0, g = 0, bh = 0, ring = 0, row_bytes = 0, slot_bytes = 0, threads = 0;
+};
+DwPlan plan_dwconv(int B, int C, int Ho, int Wo, int k, int stride, int ch) {
+  DwPlan best;
+  double best_score = -1.0;
+  for (int csl = 8; csl <= C && csl <= 256; csl += 8) {
+    if (C % csl || csl % ch) continue;
+    const int pv = csl / ch;
+    if (pv > 224) continue;
+    for (int g = 1; g * pv <= 224; ++g) {
+      const int twc = g * DW_TW, ncw = (twc - 1) * stride + k;
+      if (ncw > 256) break;
+      const int row_bytes = ncw * csl * 2;
+      if (row_bytes > 24 * 1024) break;
+      const int n_ct = ceil_div(Wo, twc), warps = ceil_div(pv * g, 32);
+      double score = ((double)Wo * stride / ((double)n_ct * ncw)) * ((double)pv * g / (warps * 32.0));
+      if (pv * g < 128) score *= 0.5 + pv * g / 256.0;  // small CTAs hide less latency
+      score += 1e-6 * row_bytes / 1024.0;                 // tie-break: larger boxes
+      if (score > best_score) {
+        best_score = score;
+        best.csl = csl; best.pv = pv; best.g = g; best.row_bytes = row_bytes;
+        best.slot_bytes = (row_bytes + 127) / 128 * 128;
+        best.threads = (warps + 1) * 32;
+      }
+    }
+  }
+  if (best.csl == 0) return best;
+  // band height: the whole column when that still leaves >= 4 tiles per resident CTA, else split (each band re-reads k - stride rows)
+  const long long want = 4LL * 2 * num_sms();
+  int bh = Ho;
+  auto tiles = [&](int h) { return (long long)B * (C / best.csl) * ceil_div(Wo, best.g * DW_TW) * ceil_div(Ho, h); };
+  while (bh > 8 && tiles(bh) < want) bh = (bh + 1) / 2;
+  best.bh = bh;
+  int ring = 96 * 1024 / best.slot_bytes;
+  best.ring = ring > DW_MAX_RING ? DW_MAX_RING : (ring < 2 ? 2 : ring);
+  return best;
+}
+
+template <int K, int S, int CH>
+int launch_dwconv_tma(const __nv_bfloat16* in, int B, int H, int W, int C, int Ho, int Wo, const DwPlan& p, const float* wkk,
+                      const float* scale, const float* shift, __nv_bfloat16* out, unsigned long long* se_sum, cudaStream_t st) {
+  DwTmaArgs a;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.Ho = Ho; a.Wo = Wo;
+  a.csl = p.csl; a.pv = p.pv; a.g = p.g; a.bh = p.bh;
+  a.n_cs = C / p.csl; a.n_ct = ceil_div(Wo, p.g * DW_TW); a.n_band = ceil_div(Ho, p.bh);
+  a.n_tiles = B * a.n_cs * a.n_ct * a.n_band;
+  a.ring = p.ring; a.slot_bytes = p.slot_bytes; a.row_bytes = p.row_bytes; a.out_row_pitch = Wo * C;
+  a.wkk = wkk; a.scale = scale; a.shift = shift; a.out = out; a.se_sum = se_sum;
+  CUtensorMap map;
+  const int ncw = (p.g * DW_TW - 1) * S + K;
+  int rc = make_tmap_nhwc16(&map, in, B, H, W, C, p.csl, ncw);
+  if (rc) return rc;
+  const size_t smem = 128 + (size_t)p.ring * p.slot_bytes + 2 * DW_MAX_RING * 8 + 2 * (size_t)p.csl * 8;
+  static bool attr_set[64] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
+    AVEXK_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<K, S, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set[dev] = true;
+  }
+  const int grid = a.n_tiles < 2 * num_sms() ? a.n_tiles : 2 * num_sms();
+  dwconv_tma_kernel<K, S, CH><<<grid, p.threads, smem, st>>>(map, a);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
 int launch_dwconv(const __nv_bfloat16* in, int B, int H, int W, int C, int k, int stride, const float* wkk, const float* scale,
                   const float* shift, __nv_bfloat16* out, unsigned long long* se_sum, cudaStream_t st) {
   AVEXK_CHECK_ARG(C % 8 == 0 && C / 8 <= 256 && (k == 3 || k == 5) && (stride == 1 || stride == 2), "dwconv: unsupported C=%d k=%d stride=%d", C, k, stride);
   if (B == 0) return AVEXK_OK;
   const int Ho = conv_out(H, k, stride), Wo = conv_out(W, k, stride);
+  // AVEXK_DW_OLD=1 (measurement switch) runs the per-output-row kernel, which is also the fallback for shapes the TMA tiling
+  // cannot express
+  static const int use_old = [] { const char* e = getenv("AVEXK_DW_OLD"); return e ? atoi(e) : 0; }();
+  if (!use_old) {
+    // 3x3: four channels per thread (8-byte shared loads, half the threads per tile); 5x5: two (the 25 weight pairs + 20
+    // accumulator pairs of four channels would not fit the register file at two CTAs per SM)
+    const int ch = k == 3 ? 4 : 2;
+    const DwPlan p = plan_dwconv(B, C, Ho, Wo, k, stride, ch);
+    if (p.csl != 0) {
+#define AVEXK_DW(K_, S_, CH_) launch_dwconv_tma<K_, S_, CH_>(in, B, H, W, C, Ho, Wo, p, wkk, scale, shift, out, se_sum, st)
+      if (k == 3 && stride == 1) return AVEXK_DW(3, 1, 4);
+      if (k == 3) return AVEXK_DW(3, 2, 4);
+      if (stride == 1) return AVEXK_DW(5, 1, 2);
+      return AVEXK_DW(5, 2, 2);
+#undef AVEXK_DW
+    }
+  }
   const int nquads = Ho * ceil_div(Wo, DW_TW);
   // pixel quads per CTA: enough work per CTA to amortise its fixed cost (zeroing / flushing the squeeze-excitation sums, two
   // barriers), few enough CTAs-worth to keep every SM busy.  AVEXK_DW_QUADS overrides (measurement).

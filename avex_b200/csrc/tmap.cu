@@ -110,4 +110,26 @@ int make_tmap_3d_bf16(CUtensorMap* map, const void* base, long long d0, long lon
   return AVEXK_OK;
 }
 
+int make_tmap_nhwc16(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_c, int box_w) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return AVEXK_ECUDA;
+  }
+  AVEXK_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 8 == 0 && box_c % 8 == 0 && box_c <= 256 && box_w <= 256,
+                  "TMA NHWC operand: 16-byte alignment / box limits (C=%d box_c=%d box_w=%d)", C, box_c, box_w);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(nhwc) failed with CUresult %d", (int)r);
+    return AVEXK_ECUDA;
+  }
+  return AVEXK_OK;
+}
+
 }  // namespace avexk

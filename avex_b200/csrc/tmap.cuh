@@ -18,4 +18,8 @@ int make_tmap_2d_64B(CUtensorMap* map, const void* base, long long rows, long lo
 int make_tmap_3d_bf16(CUtensorMap* map, const void* base, long long d0, long long d1, long long d2, long long ld1,
                       long long ld2, int b0, int b1, int b2, bool swizzle128);
 
+// 16-bit NHWC activations [B, H, W, C] as a 4-D map (C innermost); box = [1, 1, box_w, box_c], no swizzle.  Coordinates outside
+// the image (negative or >= W / H) read as zero: the zero padding of a convolution costs nothing.
+int make_tmap_nhwc16(CUtensorMap* map, const void* base, int B, int H, int W, int C, int box_c, int box_w);
+
 }  // namespace avexk

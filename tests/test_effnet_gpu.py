@@ -95,7 +95,11 @@ def test_conv1x1(lib, M, N, K, silu, res):
 
 
 @pytest.mark.parametrize("B,H,W,C,k,stride", [(2, 64, 51, 32, 3, 1), (1, 64, 101, 96, 3, 2), (3, 32, 26, 144, 5, 2),
-                                              (2, 8, 7, 480, 5, 1), (2, 4, 4, 1152, 3, 1), (1, 9, 13, 240, 3, 2)])
+                                              (2, 8, 7, 480, 5, 1), (2, 4, 4, 1152, 3, 1), (1, 9, 13, 240, 3, 2),
+                                              # the 5 s bench shapes whose tiling spans several column tiles / bands / slices
+                                              (2, 64, 250, 32, 3, 1), (1, 64, 250, 96, 3, 2), (2, 32, 125, 144, 5, 2),
+                                              (2, 16, 63, 240, 5, 1), (3, 8, 32, 672, 5, 2), (5, 4, 16, 1152, 5, 1),
+                                              (1, 70, 300, 40, 3, 1), (1, 33, 17, 24, 5, 1)])
 def test_dwconv(lib, B, H, W, C, k, stride):
     g = torch.Generator(device="cuda").manual_seed(C + k)
     x = torch.randn(B, H, W, C, device="cuda", generator=g).to(torch.float16)
