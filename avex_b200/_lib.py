@@ -119,6 +119,7 @@ SIGNATURES.update({
     "avexk_melspec_num_frames": (_i, [_i]),
     "avexk_melspec_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp, _vp, _vp]),
     "avexk_conv1x1_f16": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
+    "avexk_conv1x1_se_f16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "avexk_dwconv_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "avexk_effnet_create": (_i, [C.POINTER(EffnetBlockCfg), _i, _i, _i, C.POINTER(_vp)]),
     "avexk_effnet_destroy": (None, [_vp]),

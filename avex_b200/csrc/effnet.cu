@@ -280,23 +280,24 @@ struct DwTmaArgs {
   int B, H, W, C, Ho, Wo;
   int csl, pv, g;            // channels per tile, channel vectors (of CH) per column group, column groups per tile
   int bh;                    // output rows per band
-  int n_cs, n_ct, n_band;    // tiles per clip: channel slices x column tiles x bands
+  int n_cs, n_ct, n_band;    // channel slices; column tiles and bands per clip
   int n_tiles, ring, slot_bytes, row_bytes, out_row_pitch;
   const float *wkk, *scale, *shift;
   __nv_bfloat16* out;
   unsigned long long* se_sum;
 };
 struct DwTile {
-  int b, cs, ct, band;
+  int b, ct, band;
 };
-__device__ __forceinline__ DwTile dw_decode(int tile, const DwTmaArgs& a) {  // channel slice slowest: a CTA rarely changes weights
+// A CTA keeps ONE channel slice (blockIdx.x % n_cs: its weights are loaded once) and strides over the (clip, band, column tile)
+// positions; CTAs with consecutive blockIdx work on the other slices of the same position at the same time, so the slices of
+// a pixel -- which share DRAM sectors / L2 lines -- are fetched from DRAM once.
+__device__ __forceinline__ DwTile dw_decode(int sp, const DwTmaArgs& a) {
   DwTile t;
-  t.ct = tile % a.n_ct;
-  tile /= a.n_ct;
-  t.band = tile % a.n_band;
-  tile /= a.n_band;
-  t.b = tile % a.B;
-  t.cs = tile / a.B;
+  t.ct = sp % a.n_ct;
+  sp /= a.n_ct;
+  t.band = sp % a.n_band;
+  t.b = sp / a.n_band;
   return t;
 }
 
@@ -331,8 +332,9 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const DwTile t = dw_decode(tile, a);
+      const int cs = blockIdx.x % a.n_cs;
+      for (int sp = blockIdx.x / a.n_cs; sp < a.n_tiles; sp += gridDim.x / a.n_cs) {
+        const DwTile t = dw_decode(sp, a);
         const int ho0 = t.band * a.bh, rows = min(a.bh, a.Ho - ho0);
         const int hi0 = ho0 * S - PAD, wi0 = t.ct * a.g * TW * S - PAD, nsteps = (rows - 1) * S + K;
         for (int r = 0; r < nsteps; ++r) {
@@ -340,7 +342,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
           if ((unsigned)hi >= (unsigned)a.H) continue;  // a padding row: the consumers know, nothing is sent
           ptx::mbar_wait_a(empty_a + slot * 8, phase ^ 1);
           ptx::mbar_arrive_expect_tx_a(full_a + slot * 8, a.row_bytes);
-          ptx::tma_load_4d_a(ring_a + slot * a.slot_bytes, &map_in, full_a + slot * 8, t.cs * a.csl, wi0, hi, t.b);
+          ptx::tma_load_4d_a(ring_a + slot * a.slot_bytes, &map_in, full_a + slot * 8, cs * a.csl, wi0, hi, t.b);
           if (++slot == a.ring) { slot = 0; phase ^= 1; }
         }
       }
@@ -354,23 +356,20 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
   const int cvv = active ? tid % a.pv : 0, cg = active ? tid / a.pv : 0;  // idle threads shadow thread 0 (no stores)
   const uint32_t x_off = ((cg * TW * S) * a.csl + cvv * CH) * 2;          // this thread's first column inside a ring row
   const uint32_t col_pitch = a.csl * 2;
-  int slot = 0, last_cs = -1, tile_par = 0;
+  int slot = 0, tile_par = 0;
   uint32_t phase = 0;
+  const int cs = blockIdx.x % a.n_cs, c0 = cs * a.csl + cvv * CH;
   float2 w[K * K][V], sh[V];  // BatchNorm folded: w = conv weight * scale, accumulators start from the shift
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, tile_par ^= 1) {
-    const DwTile t = dw_decode(tile, a);
-    const int c0 = t.cs * a.csl + cvv * CH;
-    if (t.cs != last_cs) {  // (CTA-uniform)
-      last_cs = t.cs;
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const float2 sc = __ldg(reinterpret_cast<const float2*>(a.scale + c0 + 2 * v));
-        sh[v] = __ldg(reinterpret_cast<const float2*>(a.shift + c0 + 2 * v));
+  for (int v = 0; v < V; ++v) {
+    const float2 sc = __ldg(reinterpret_cast<const float2*>(a.scale + c0 + 2 * v));
+    sh[v] = __ldg(reinterpret_cast<const float2*>(a.shift + c0 + 2 * v));
 #pragma unroll
-        for (int kk = 0; kk < K * K; ++kk)
-          w[kk][v] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(a.wkk + (size_t)kk * a.C + c0 + 2 * v)), sc);
-      }
-    }
+    for (int kk = 0; kk < K * K; ++kk)
+      w[kk][v] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(a.wkk + (size_t)kk * a.C + c0 + 2 * v)), sc);
+  }
+  for (int sp = blockIdx.x / a.n_cs; sp < a.n_tiles; sp += gridDim.x / a.n_cs, tile_par ^= 1) {
+    const DwTile t = dw_decode(sp, a);
     const int ho0 = t.band * a.bh, rows = min(a.bh, a.Ho - ho0), wo0 = (t.ct * a.g + cg) * TW;
     const int hi0 = ho0 * S - PAD, r_last = (rows - 1) * S + K - 1;
     const int nvalid = active ? a.Wo - wo0 : 0;  // output columns tt < nvalid are stored
@@ -455,7 +454,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
       }
       ptx::named_bar_sync(1, n_cons);
       for (int i = tid; i < a.csl; i += n_cons) {
-        atomicAdd(a.se_sum + (size_t)t.b * a.C + t.cs * a.csl + i, sb[i]);
+        atomicAdd(a.se_sum + (size_t)t.b * a.C + cs * a.csl + i, sb[i]);
         sb[i] = 0ull;  // this buffer is next written two tiles from now, behind the next tile's barrier
       }
     }
@@ -643,7 +642,7 @@ int launch_dwconv_tma(const __nv_bfloat16* in, int B, int H, int W, int C, int H
   a.B = B; a.H = H; a.W = W; a.C = C; a.Ho = Ho; a.Wo = Wo;
   a.csl = p.csl; a.pv = p.pv; a.g = p.g; a.bh = p.bh;
   a.n_cs = C / p.csl; a.n_ct = ceil_div(Wo, p.g * DW_TW); a.n_band = ceil_div(Ho, p.bh);
-  a.n_tiles = B * a.n_cs * a.n_ct * a.n_band;
+  a.n_tiles = B * a.n_ct * a.n_band;  // positions; each is worked on by n_cs CTAs
   a.ring = p.ring; a.slot_bytes = p.slot_bytes; a.row_bytes = p.row_bytes; a.out_row_pitch = Wo * C;
   a.wkk = wkk; a.scale = scale; a.shift = shift; a.out = out; a.se_sum = se_sum;
   CUtensorMap map;
@@ -657,7 +656,10 @@ int launch_dwconv_tma(const __nv_bfloat16* in, int B, int H, int W, int C, int H
     AVEXK_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<K, S, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_set[dev] = true;
   }
-  const int grid = a.n_tiles < 2 * num_sms() ? a.n_tiles : 2 * num_sms();
+  int per_slice = 2 * num_sms() / a.n_cs;  // CTAs per channel slice (two CTAs per SM are resident)
+  if (per_slice < 1) per_slice = 1;
+  if (per_slice > a.n_tiles) per_slice = a.n_tiles;
+  const int grid = per_slice * a.n_cs;
   dwconv_tma_kernel<K, S, CH><<<grid, p.threads, smem, st>>>(map, a);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
@@ -702,6 +704,24 @@ int launch_dwconv(const __nv_bfloat16* in, int B, int H, int W, int C, int k, in
   return AVEXK_OK;
 }
 
+// 1x1 convolution dispatch: the memory-bound kernel (pointwise.cu) whenever the request fits it (fp16 output, no raw copy);
+// the general GEMM otherwise.  AVEXK_PW=0 (measurement switch) forces the general GEMM.  A squeeze-excitation scale on the A
+// operand is fused by the pointwise kernel; on the general path it is applied in place first.
+int conv1x1_any(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
+                const __nv_bfloat16* res, const float* se_scale, int hw, float* raw_out, void* out, int out_16bit, cudaStream_t st) {
+  static const int use_pw = [] { const char* e = getenv("AVEXK_PW"); return e ? atoi(e) : 1; }();
+  if (use_pw && pointwise_supported(N, K, raw_out, out, out_16bit))
+    return pointwise_launch(A, W, M, N, K, scale, shift, silu, res, se_scale, hw, out, st);
+  if (se_scale != nullptr && M > 0) {
+    const long long per_clip_vec = (long long)hw * (K / 8), total = (long long)M * (K / 8);
+    int grid = ceil_div(total, 256);
+    if (grid > num_sms() * 16) grid = num_sms() * 16;
+    se_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(A)), se_scale, per_clip_vec, K / 8, total);
+    AVEXK_LAUNCH_CHECK();
+  }
+  return conv1x1_launch(A, W, M, N, K, scale, shift, silu, res, raw_out, out, out_16bit, st);
+}
+
 }  // namespace avexk
 
 // ============================================================================================================
@@ -711,8 +731,17 @@ extern "C" int avexk_conv1x1_f16(const void* A, const void* W, int M, int N, int
                                   int silu, const void* res_bf16, float* raw_out, void* out, int out_bf16, void* stream) {
   using namespace avexk;
   AVEXK_CHECK_ARG(A && W && (out || raw_out) && M >= 0, "avexk_conv1x1_f16: null argument");
-  return conv1x1_launch(A, W, M, N, K, scale, shift, silu, reinterpret_cast<const __nv_bfloat16*>(res_bf16), raw_out, out, out_bf16,
-                        reinterpret_cast<cudaStream_t>(stream));
+  return conv1x1_any(A, W, M, N, K, scale, shift, silu, reinterpret_cast<const __nv_bfloat16*>(res_bf16), nullptr, 0, raw_out, out,
+                     out_bf16, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int avexk_conv1x1_se_f16(const void* A, const float* se_scale, int rows_per_clip, const void* W, int M, int N, int K,
+                                     const float* scale, const float* shift, const void* res_f16, void* out, void* stream) {
+  using namespace avexk;
+  AVEXK_CHECK_ARG(A && W && out && se_scale && M >= 0 && rows_per_clip > 0, "avexk_conv1x1_se_f16: bad argument");
+  AVEXK_CHECK_ARG(pointwise_supported(N, K, nullptr, out, 1), "avexk_conv1x1_se_f16: K and N must be multiples of 8 (K=%d N=%d)", K, N);
+  return pointwise_launch(A, W, M, N, K, scale, shift, 0, reinterpret_cast<const __nv_bfloat16*>(res_f16), se_scale, rows_per_clip, out,
+                          reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int avexk_dwconv_nhwc(const void* in_bf16, int B, int H, int W, int C, int k, int stride, const float* w_ckk,
@@ -909,7 +938,7 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
     const long long M = (long long)B * H * W;
     const __nv_bfloat16* dw_in = act;
     if (b.expand_w != nullptr) {
-      TRY(conv1x1_launch(act, b.expand_w, (int)M, c.cexp, c.cin, b.expand_scale, b.expand_shift, 1, nullptr, nullptr, ex, 1, st));
+      TRY(conv1x1_any(act, b.expand_w, (int)M, c.cexp, c.cin, b.expand_scale, b.expand_shift, 1, nullptr, nullptr, 0, nullptr, ex, 1, st));
       dw_in = ex;
     }
     const int Ho = conv_out(H, c.kernel, c.stride), Wo = conv_out(W, c.kernel, c.stride);
@@ -918,18 +947,12 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
     se_mlp_kernel<<<B, 256, (c.cexp + c.csq) * sizeof(float), st>>>(se_sum, 1.0f / (float)(Ho * Wo), c.cexp, c.csq, b.se1_w, b.se1_b,
                                                                     b.se2_w, b.se2_b, se_scale);
     AVEXK_LAUNCH_CHECK();
-    {
-      const long long per_clip_vec = (long long)Ho * Wo * (c.cexp / 8), total = per_clip_vec * B;
-      int grid = ceil_div(total, 256);
-      if (grid > 148 * 16) grid = 148 * 16;
-      se_apply_kernel<<<grid, 256, 0, st>>>(dw, se_scale, per_clip_vec, c.cexp / 8, total);
-      AVEXK_LAUNCH_CHECK();
-    }
     const long long Mo = (long long)B * Ho * Wo;
     const bool use_res = c.stride == 1 && c.cin == c.cout;
     float* hook = hook_out ? hook_out[1 + i] : nullptr;
-    TRY(conv1x1_launch(dw, b.proj_w, (int)Mo, c.cout, c.cexp, b.proj_scale, b.proj_shift, 0, use_res ? act : nullptr,
-                       hook ? raw : nullptr, act2, 1, st));
+    // project conv; the squeeze-excitation rescale of its input rides on the A operand (or runs in place first on the hook path)
+    TRY(conv1x1_any(dw, b.proj_w, (int)Mo, c.cout, c.cexp, b.proj_scale, b.proj_shift, 0, use_res ? act : nullptr, se_scale, Ho * Wo,
+                    hook ? raw : nullptr, act2, 1, st));
     if (hook) TRY(to_nchw(raw, Ho * Wo, c.cout, hook));
     std::swap(act, act2);
     H = Ho;

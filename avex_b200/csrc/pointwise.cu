@@ -1,0 +1,357 @@
+// pointwise.cu -- the 1x1 convolutions of EfficientNet as a memory-bound tcgen05 kernel.
+//
+// out[M, N] = act((se[row / hw, :] * A[M, K]) @ W[N, K]^T * scale + shift) (+ res), A / W / res / out fp16, fp32 accumulation.
+// Replaces torchvision `Conv2dNormActivation(kernel_size=1)` + BatchNorm(eval) + SiLU inside `MBConv` and, for the project
+// convolution, the squeeze-excitation rescale `scale * input` that precedes it (called from efficientnet.py:163-215).
+//
+// These GEMMs have K and N in 16..1152 and M up to 8.2 M rows: 0.3 .. 30 FLOP per byte, i.e. HBM-bound.  The general GEMM of
+// gemm_tc.cu (256-wide tiles, two accumulator stages, sixteen epilogue warps polling) spends ~6600 cycles per 256-row tile on
+// them; this kernel is built around bytes in flight and instructions per output element instead:
+//   * persistent CTA, 128-row tiles; one TMA producer thread keeps a ring of A k-blocks (and W k-blocks when W does not fit)
+//     in flight; W stays resident in shared memory when it fits (every layer of the high-resolution stages);
+//   * one MMA thread issues kind::f16 UMMAs (M = 128, N = the layer's N rounded to 16) into a ring of up to eight TMEM
+//     accumulators, so the epilogue of tile t overlaps the loads and MMAs of tiles t+1 .. t+7;
+//   * eight epilogue warps (two per TMEM lane quarter) read 8-column chunks, apply BatchNorm / SiLU / residual with packed
+//     fp32x2 arithmetic, and park the fp16 row in a padded shared-memory tile; each row then leaves with ONE bulk copy
+//     (cp.async.bulk shared -> global): full-line writes, no per-thread scattered stores;
+//   * squeeze-excitation: four "scaler" warps multiply the A tile by the clip's channel scale in shared memory before the
+//     MMA reads it -- the separate read-modify-write pass over the depthwise output (se_apply_kernel) disappears.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace avexk {
+namespace {
+
+constexpr int PW_BM = 128, PW_BK = 64, PW_A_BYTES = PW_BM * PW_BK * 2;
+constexpr int PW_MAX_STAGES = 8, PW_MAX_ACC = 8;
+constexpr int PW_WARP_LOAD = 0, PW_WARP_MMA = 1, PW_WARP_SCALE0 = 2, PW_WARP_EPI0 = 6, PW_THREADS = 14 * 32;
+constexpr int PW_EPI_THREADS = 256;
+
+struct PwArgs {
+  int M, N, K;
+  int ntb, n_nt;           // N tile (multiple of 16, <= 256) and number of N tiles
+  int kblocks;             // ceil(K / 64)
+  int stages, stage_bytes; // ring depth; bytes per stage (A block, + W block when W is streamed)
+  int w_resident, w_block_bytes;
+  int acc_stride, acc_stages;
+  int ob_pitch;            // bytes per row of the output staging tile (ntb * 2 + 16: conflict-free 16-byte row writes)
+  int off_w, off_ob, off_tab, off_bar;
+  uint32_t idesc;
+  int m_tiles, silu, hw;
+  const float *scale, *shift, *se_scale;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* out;
+};
+
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// silu for a pair: one packed multiply, two EX2, one packed add, two RCP, one packed multiply
+__device__ __forceinline__ float2 pw_silu2(float2 v) {
+  const float2 q = __fmul2_rn(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  e = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+  return __fmul2_rn(v, r);
+}
+
+__global__ void __launch_bounds__(PW_THREADS, 1)
+pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const PwArgs g) {
+  extern __shared__ unsigned char pw_smem_raw[];
+  unsigned char* smem = pw_smem_raw + ((1024u - (ptx::smem_u32(pw_smem_raw) & 1023u)) & 1023u);
+  const uint32_t smem_a = ptx::smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+  uint64_t* a_full = bars;                          // [PW_MAX_STAGES]  TMA landed
+  uint64_t* a_ready = bars + PW_MAX_STAGES;         // [PW_MAX_STAGES]  scaled (SE mode): what the MMA thread waits on
+  uint64_t* a_empty = bars + 2 * PW_MAX_STAGES;     // [PW_MAX_STAGES]  MMAs reading the stage have completed
+  uint64_t* t_full = bars + 3 * PW_MAX_STAGES;      // [PW_MAX_ACC]
+  uint64_t* t_empty = t_full + PW_MAX_ACC;          // [PW_MAX_ACC]
+  uint64_t* w_full = t_empty + PW_MAX_ACC;          // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* tab = reinterpret_cast<float*>(smem + g.off_tab);  // scale[N], shift[N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool se = g.se_scale != nullptr;
+  const int n_tiles = g.m_tiles * g.n_nt;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_w);
+    for (int s = 0; s < g.stages; ++s) {
+      ptx::mbar_init(&a_full[s], 1);
+      ptx::mbar_init(&a_ready[s], 4);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < g.acc_stages; ++s) {
+      ptx::mbar_init(&t_full[s], 1);
+      ptx::mbar_init(&t_empty[s], PW_EPI_THREADS / 32);
+    }
+    ptx::mbar_init(w_full, 1);
+    ptx::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < g.N; i += blockDim.x) {
+    tab[i] = g.scale != nullptr ? __ldg(g.scale + i) : 1.0f;
+    tab[g.N + i] = g.shift != nullptr ? __ldg(g.shift + i) : 0.0f;
+  }
+  if (warp == PW_WARP_MMA) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == PW_WARP_LOAD) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (g.w_resident) {
+        ptx::mbar_arrive_expect_tx(w_full, g.kblocks * g.w_block_bytes);
+        for (int kb = 0; kb < g.kblocks; ++kb) ptx::tma_load_2d(smem + g.off_w + kb * g.w_block_bytes, &map_w, w_full, kb * PW_BK, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / g.n_nt, nt = tile - mt * g.n_nt;
+        for (int kb = 0; kb < g.kblocks; ++kb) {
+          ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+          unsigned char* dst = smem + stage * g.stage_bytes;
+          ptx::mbar_arrive_expect_tx(&a_full[stage], g.stage_bytes);
+          ptx::tma_load_2d(dst, &map_a, &a_full[stage], kb * PW_BK, mt * PW_BM);
+          if (!g.w_resident) ptx::tma_load_2d(dst + PW_A_BYTES, &map_w, &a_full[stage], kb * PW_BK, nt * g.ntb);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == PW_WARP_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      if (g.w_resident) {
+        ptx::mbar_wait(w_full, 0);
+        ptx::tc_fence_after();
+      }
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * g.acc_stride;
+        for (int kb = 0; kb < g.kblocks; ++kb) {
+          ptx::mbar_wait(se ? &a_ready[stage] : &a_full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_a + stage * g.stage_bytes;
+          const uint32_t sb = g.w_resident ? smem_a + g.off_w + kb * g.w_block_bytes : sa + PW_A_BYTES;
+          const uint64_t da = ptx::make_sw128_desc(sa), db = ptx::make_sw128_desc(sb);
+          const int ksteps = min(PW_BK, g.K - kb * PW_BK + 15) / 16;  // the zero-filled tail of the last k-block is skipped
+          for (int k = 0; k < ksteps; ++k) ptx::umma_bf16(d_tmem, da + 2 * k, db + 2 * k, g.idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit(&a_empty[stage]);
+          if (kb == g.kblocks - 1) ptx::umma_commit(&t_full[acc]);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == g.acc_stages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < PW_WARP_EPI0) {
+    // ===================== squeeze-excitation scalers: A[row, :] *= se[clip(row), :] in shared memory =====================
+    if (se) {
+      const int row = threadIdx.x - PW_WARP_SCALE0 * 32;  // 0..127: one A row per thread
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / g.n_nt, grow = mt * PW_BM + row;
+        const float* sp = g.se_scale + (size_t)(grow < g.M ? grow / g.hw : 0) * g.K;
+        for (int kb = 0; kb < g.kblocks; ++kb) {
+          ptx::mbar_wait(&a_full[stage], phase);
+          if (grow < g.M) {
+            const uint32_t rowa = smem_a + stage * g.stage_bytes + row * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = (i + row) & 7;                       // rotate: the 8 lanes of a quarter-warp hit 8 bank groups
+              const int col = kb * PW_BK + ((j ^ (row & 7)) << 3);  // logical k of this 16-byte chunk (128-byte swizzle)
+              if (col < g.K) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp + col)), s1 = __ldg(reinterpret_cast<const float4*>(sp + col + 4));
+                uint4 v = lds128u(rowa + j * 16);
+                float2 a = unpack_h16(v.x), b = unpack_h16(v.y), c = unpack_h16(v.z), d = unpack_h16(v.w);
+                v.x = pack_h16(a.x * s0.x, a.y * s0.y);
+                v.y = pack_h16(b.x * s0.z, b.y * s0.w);
+                v.z = pack_h16(c.x * s1.x, c.y * s1.y);
+                v.w = pack_h16(d.x * s1.z, d.y * s1.w);
+                sts128u(rowa + j * 16, v);
+              }
+            }
+          }
+          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (8 warps: TMEM lane quarter x column half) =====================
+    const int ew = warp - PW_WARP_EPI0, quarter = warp & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;
+    const int half_cols = g.ntb >> 1, nch = half_cols >> 3;  // 8-column chunks per thread and tile
+    const uint32_t tab_a = smem_a + g.off_tab;
+    int acc = 0, par = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+      const int mt = tile / g.n_nt, nt = tile - mt * g.n_nt;
+      const int grow = mt * PW_BM + row, n0 = nt * g.ntb + half * half_cols;
+      const uint32_t ob_row = smem_a + g.off_ob + par * (PW_BM * g.ob_pitch) + row * g.ob_pitch + half * half_cols * 2;
+      const __nv_bfloat16* resp = g.res != nullptr && grow < g.M ? g.res + (size_t)grow * g.N + n0 : nullptr;
+      ptx::mbar_wait(&t_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * g.acc_stride + half * half_cols;
+
+      auto process = [&](const uint32_t (&v)[8], int i) {
+        const int col = n0 + i * 8;
+        if (col >= g.N) return;  // (warp-uniform) zero-padded columns of the last N tile
+        const float4 sc0 = lds128f(tab_a + col * 4), sc1 = lds128f(tab_a + col * 4 + 16);
+        const float4 sh0 = lds128f(tab_a + (g.N + col) * 4), sh1 = lds128f(tab_a + (g.N + col) * 4 + 16);
+        float2 y0 = __ffma2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
+        float2 y1 = __ffma2_rn(make_float2(__uint_as_float(v[2]), __uint_as_float(v[3])), make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
+        float2 y2 = __ffma2_rn(make_float2(__uint_as_float(v[4]), __uint_as_float(v[5])), make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
+        float2 y3 = __ffma2_rn(make_float2(__uint_as_float(v[6]), __uint_as_float(v[7])), make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
+        if (g.silu) {
+          y0 = pw_silu2(y0); y1 = pw_silu2(y1); y2 = pw_silu2(y2); y3 = pw_silu2(y3);
+        }
+        if (resp != nullptr) {
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + i * 8));
+          y0 = __fadd2_rn(y0, unpack_h16(rv.x)); y1 = __fadd2_rn(y1, unpack_h16(rv.y));
+          y2 = __fadd2_rn(y2, unpack_h16(rv.z)); y3 = __fadd2_rn(y3, unpack_h16(rv.w));
+        }
+        sts128u(ob_row + i * 16, make_uint4(pack_h16(y0.x, y0.y), pack_h16(y1.x, y1.y), pack_h16(y2.x, y2.y), pack_h16(y3.x, y3.y)));
+      };
+
+      uint32_t va[8], vb[8];
+      tmem_ld_32x8(t_addr, va);
+      for (int i = 0; i < nch; i += 2) {
+        ptx::tmem_ld_wait();
+        if (i + 1 < nch) tmem_ld_32x8(t_addr + (i + 1) * 8, vb);
+        else {  // every TMEM read of this accumulator has completed: hand it back to the MMA thread before the last chunk's math
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+        }
+        process(va, i);
+        if (i + 1 < nch) {
+          ptx::tmem_ld_wait();
+          if (i + 2 < nch) tmem_ld_32x8(t_addr + (i + 2) * 8, va);
+          else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+          }
+          process(vb, i + 1);
+        }
+      }
+      if (++acc == g.acc_stages) { acc = 0; acc_phase ^= 1; }
+
+      // the tile is parked in shared memory: one bulk copy per row (issued by the row's half-0 thread).  The staging buffer
+      // of the PREVIOUS tile is free once that thread's earlier copy has finished reading -- checked before the barrier.
+      ptx::fence_proxy_async();
+      if (half == 0) ptx::tma_store_wait_read();
+      ptx::named_bar_sync(1, PW_EPI_THREADS);
+      if (half == 0 && grow < g.M) {
+        const int nvalid = min(g.ntb, g.N - nt * g.ntb);
+        bulk_store(g.out + (size_t)grow * g.N + nt * g.ntb, ob_row, nvalid * 2);
+        ptx::tma_store_commit();
+      }
+    }
+    if (half == 0) ptx::tma_store_wait_all();  // the copies must have been performed before the CTA exits
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == PW_WARP_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// Whether the memory-bound kernel takes this 1x1 convolution (else the general GEMM does): fp16 output, no raw (pre-BN) copy.
+bool pointwise_supported(int N, int K, const float* raw_out, const void* out, int out_16bit) {
+  return raw_out == nullptr && out != nullptr && out_16bit && N % 8 == 0 && K % 8 == 0 && N >= 8 && K >= 8;
+}
+
+int pointwise_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
+                     const __nv_bfloat16* res, const float* se_scale, int hw, void* out, cudaStream_t st) {
+  AVEXK_CHECK_ARG(pointwise_supported(N, K, nullptr, out, 1), "pointwise: unsupported shape N=%d K=%d", N, K);
+  AVEXK_CHECK_ARG(se_scale == nullptr || hw > 0, "pointwise: squeeze-excitation scale needs rows per clip");
+  if (M == 0) return AVEXK_OK;
+  PwArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.kblocks = ceil_div(K, PW_BK);
+  // N tiling: one tile when N <= 256, else the fewest tiles of <= 160 columns (keeps three 36 KB stages + two staging tiles)
+  const int n16 = (N + 15) / 16 * 16;
+  if (n16 <= 256) { g.n_nt = 1; g.ntb = n16; }
+  else { g.n_nt = ceil_div(N, 160); g.ntb = (ceil_div(N, g.n_nt) + 15) / 16 * 16; }
+  g.w_block_bytes = g.ntb * 128;
+  g.ob_pitch = g.ntb * 2 + 16;
+  const int ob_bytes = 2 * PW_BM * g.ob_pitch, tab_bytes = (2 * N * 4 + 15) / 16 * 16;
+  const int bar_bytes = (3 * PW_MAX_STAGES + 2 * PW_MAX_ACC + 1) * 8 + 16;
+  const int budget = 227 * 1024 - 1024 - ob_bytes - tab_bytes - bar_bytes - 128;
+  const int w_all = g.kblocks * g.w_block_bytes;
+  g.w_resident = g.n_nt == 1 && budget - w_all >= 4 * PW_A_BYTES;
+  g.stage_bytes = PW_A_BYTES + (g.w_resident ? 0 : g.w_block_bytes);
+  int stages = (budget - (g.w_resident ? w_all : 0)) / g.stage_bytes;
+  AVEXK_CHECK_ARG(stages >= 2, "pointwise: tile does not fit shared memory (N=%d K=%d)", N, K);
+  g.stages = stages > PW_MAX_STAGES ? PW_MAX_STAGES : stages;
+  g.off_w = g.stages * g.stage_bytes;
+  g.off_ob = g.off_w + (g.w_resident ? w_all : 0);
+  g.off_tab = g.off_ob + ob_bytes;
+  g.off_bar = g.off_tab + tab_bytes;
+  g.acc_stride = (g.ntb + 31) / 32 * 32;
+  g.acc_stages = 512 / g.acc_stride > PW_MAX_ACC ? PW_MAX_ACC : 512 / g.acc_stride;
+  g.idesc = ptx::make_idesc_f16(PW_BM, g.ntb);
+  g.m_tiles = ceil_div(M, PW_BM);
+  g.silu = silu; g.hw = hw;
+  g.scale = scale; g.shift = shift; g.se_scale = se_scale; g.res = res;
+  g.out = reinterpret_cast<__nv_bfloat16*>(out);
+  CUtensorMap map_a, map_w;
+  int rc = make_tmap_2d_bf16(&map_a, A, M, K, K, PW_BM, PW_BK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&map_w, W, N, K, K, g.ntb, PW_BK);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)g.off_bar + bar_bytes;
+  static bool attr_set[64] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
+    AVEXK_CUDA(cudaFuncSetAttribute(pointwise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  const int tiles = g.m_tiles * g.n_nt;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  pointwise_kernel<<<grid, PW_THREADS, smem, st>>>(map_a, map_w, g);
+  AVEXK_LAUNCH_CHECK();
+  return AVEXK_OK;
+}
+
+}  // namespace avexk

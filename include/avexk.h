@@ -257,6 +257,13 @@ int avexk_melspec_forward(const avexk_melspec_t* h, const float* wav, int B, int
 int avexk_conv1x1_f16(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
                       const void* res_f16, float* raw_out, void* out, int out_f16, void* stream);
 
+/* The MBConv project convolution with the squeeze-excitation rescale of its input fused on the A operand
+ * (torchvision SqueezeExcitation.forward `scale * input` followed by the project Conv2dNormActivation):
+ *   out[m,n] = (sum_k se_scale[m / rows_per_clip, k] * A[m,k] * W[n,k]) * scale[n] + shift[n] (+ res[m,n]), fp16 out.
+ * se_scale [M / rows_per_clip, K] fp32; A is not modified. */
+int avexk_conv1x1_se_f16(const void* A, const float* se_scale, int rows_per_clip, const void* W, int M, int N, int K,
+                         const float* scale, const float* shift, const void* res_f16, void* out, void* stream);
+
 /* Depthwise k x k convolution (k = 3 | 5, stride 1 | 2, padding (k-1)/2) + folded BatchNorm + SiLU.
  * in [B,H,W,C] fp16, w_ckk [C,1,k,k] fp32 (torch layout), out [B,Ho,Wo,C] fp16, Ho = (H + 2p - k) / stride + 1.
  * se_sum [B,C] fp32 (may be NULL) receives sum over output pixels of the activated output (squeeze-excitation).

@@ -94,6 +94,51 @@ def test_conv1x1(lib, M, N, K, silu, res):
     assert (out.float() - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())  # fp16 output rounding
 
 
+# the MBConv shapes of the 5 s bench (rows = a few 128-row tiles + a ragged tail), project convs with the SE scale fused
+@pytest.mark.parametrize("rows_per_clip,clips,N,K,res", [(16000, 2, 16, 32, False), (4000, 3, 24, 96, False), (1008, 5, 40, 144, False),
+                                                         (1008, 5, 40, 240, True), (256, 9, 80, 480, True), (256, 9, 112, 672, True),
+                                                         (64, 37, 192, 1152, True), (64, 37, 320, 1152, False), (100, 3, 24, 144, True)])
+def test_conv1x1_se(lib, rows_per_clip, clips, N, K, res):
+    g = torch.Generator(device="cuda").manual_seed(N * K)
+    M = rows_per_clip * clips
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.float16)
+    se = torch.rand(clips, K, device="cuda", generator=g)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).to(torch.float16)
+    scale = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    shift = 0.3 * torch.randn(N, device="cuda", generator=g)
+    R = torch.randn(M, N, device="cuda", generator=g).to(torch.float16) if res else None
+    out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    A0 = A.clone()
+    _check(lib.avexk_conv1x1_se_f16(A.data_ptr(), se.data_ptr(), rows_per_clip, W.data_ptr(), M, N, K, scale.data_ptr(), shift.data_ptr(),
+                                     R.data_ptr() if res else None, out.data_ptr(), _stream()), lib)  # fmt: skip
+    assert torch.equal(A, A0)  # the rescale happens on the staged copy
+    # the kernel rounds se * A to fp16 before the tensor core, as the in-place se_apply pass did
+    As = (A.float().view(clips, rows_per_clip, K) * se[:, None, :]).to(torch.float16).float().view(M, K)
+    ref = (As @ W.float().T) * scale + shift
+    if res:
+        ref = ref + R.float()
+    assert (out.float() - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,silu", [(128 * 70 + 5, 96, 16, 1), (5000, 144, 24, 1), (3000, 240, 40, 1), (1500, 480, 80, 1),
+                                        (700, 672, 112, 1), (400, 1152, 192, 1), (333, 8, 8, 0), (1, 1280, 320, 1)])
+def test_conv1x1_wide_and_tiled(lib, M, N, K, silu):
+    """expand-conv shapes: N up to 1152 (several N tiles, W streamed), K from one partial k-block to three."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.float16)
+    W = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).to(torch.float16)
+    scale = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    shift = 0.3 * torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M + 1, N), 7.0, device="cuda", dtype=torch.float16)  # one guard row behind the output
+    _check(lib.avexk_conv1x1_f16(A.data_ptr(), W.data_ptr(), M, N, K, scale.data_ptr(), shift.data_ptr(), silu, None, None,
+                                  out.data_ptr(), 1, _stream()), lib)  # fmt: skip
+    ref = (A.float() @ W.float().T) * scale + shift
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    assert (out[:M].float() - ref).abs().max().item() <= 3e-3 * max(1.0, ref.abs().max().item())
+    assert bool((out[M] == 7.0).all())  # nothing written past row M
+
+
 @pytest.mark.parametrize("B,H,W,C,k,stride", [(2, 64, 51, 32, 3, 1), (1, 64, 101, 96, 3, 2), (3, 32, 26, 144, 5, 2),
                                               (2, 8, 7, 480, 5, 1), (2, 4, 4, 1152, 3, 1), (1, 9, 13, 240, 3, 2),
                                               # the 5 s bench shapes whose tiling spans several column tiles / bands / slices
