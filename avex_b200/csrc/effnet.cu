@@ -50,6 +50,18 @@ namespace avexk {
 namespace {
 
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
+// silu for a channel pair: one packed multiply, two EX2, two RCP (no range fix-ups: ex2.approx.ftz saturates to +inf / 0, and
+// v * rcp(1 + inf) = -0 is the right limit)
+__device__ __forceinline__ float2 silu2(float2 v) {
+  const float2 q = __fmul2_rn(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  float2 e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
+  e = __fadd2_rn(e, make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+  return __fmul2_rn(v, r);
+}
 
 __device__ __forceinline__ float dec_ordered(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
@@ -92,7 +104,7 @@ __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ mel, const unsigned* __restrict__ minmax, int B, int H, int W, int Ho, int Wo,
             const float* __restrict__ w9, const float* __restrict__ scale, const float* __restrict__ shift,
             __nv_bfloat16* __restrict__ out, float* __restrict__ raw_nchw) {
-  __shared__ float sw[9 * STEM_C], ss[STEM_C], sh[STEM_C];
+  __shared__ __align__(16) float sw[9 * STEM_C], ss[STEM_C], sh[STEM_C];
   for (int i = threadIdx.x; i < 9 * STEM_C; i += blockDim.x) sw[i] = w9[i];
   if (threadIdx.x < STEM_C) {
     ss[threadIdx.x] = scale[threadIdx.x];
@@ -118,20 +130,29 @@ stem_kernel(const float* __restrict__ mel, const unsigned* __restrict__ minmax, 
       const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
       v[ky * 3 + kx] = ok ? (__ldg(img + (size_t)hi * W + wi) - mn) * inv : 0.f;  // zero padding of the normalised image
     }
+  // four channels per step: one 16-byte broadcast read of the tap's weights feeds two packed fp32x2 FMAs
   uint32_t packed[STEM_C / 2];
 #pragma unroll
-  for (int c = 0; c < STEM_C; c += 2) {
-    float a0 = 0.f, a1 = 0.f;
+  for (int c = 0; c < STEM_C; c += 4) {
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      a0 = fmaf(v[t], sw[t * STEM_C + c], a0);
-      a1 = fmaf(v[t], sw[t * STEM_C + c + 1], a1);
+      const float4 w4 = *reinterpret_cast<const float4*>(&sw[t * STEM_C + c]);
+      const float2 x2 = make_float2(v[t], v[t]);
+      a0 = __ffma2_rn(x2, make_float2(w4.x, w4.y), a0);
+      a1 = __ffma2_rn(x2, make_float2(w4.z, w4.w), a1);
     }
     if (raw_nchw != nullptr) {
-      raw_nchw[((size_t)b * STEM_C + c) * Ho * Wo + p] = a0;
-      raw_nchw[((size_t)b * STEM_C + c + 1) * Ho * Wo + p] = a1;
+      raw_nchw[((size_t)b * STEM_C + c) * Ho * Wo + p] = a0.x;
+      raw_nchw[((size_t)b * STEM_C + c + 1) * Ho * Wo + p] = a0.y;
+      raw_nchw[((size_t)b * STEM_C + c + 2) * Ho * Wo + p] = a1.x;
+      raw_nchw[((size_t)b * STEM_C + c + 3) * Ho * Wo + p] = a1.y;
     }
-    packed[c / 2] = pack_h16(silu(fmaf(a0, ss[c], sh[c])), silu(fmaf(a1, ss[c + 1], sh[c + 1])));
+    const float4 s4 = *reinterpret_cast<const float4*>(&ss[c]), h4 = *reinterpret_cast<const float4*>(&sh[c]);
+    const float2 y0 = silu2(__ffma2_rn(a0, make_float2(s4.x, s4.y), make_float2(h4.x, h4.y)));
+    const float2 y1 = silu2(__ffma2_rn(a1, make_float2(s4.z, s4.w), make_float2(h4.z, h4.w)));
+    packed[c / 2] = pack_h16(y0.x, y0.y);
+    packed[c / 2 + 1] = pack_h16(y1.x, y1.y);
   }
   uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * Ho * Wo + p) * STEM_C);
 #pragma unroll
@@ -244,18 +265,6 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ in, int H, int W, int C, int Ho,
 // over one period of that rotation, so every slot index is a compile-time constant).  Two channels ride in one packed fp32x2
 // FMA.  Against the per-output-row kernel above: K (stride 1) or K/2 (stride 2) times fewer loads per output, no weight
 // traffic, no address arithmetic in the row loop -- the layers become DRAM / FMA-issue bound instead of LSU bound.
-// silu for a channel pair: one packed multiply, two EX2, two RCP (no range fix-ups: ex2.approx.ftz saturates to +inf / 0, and
-// v * rcp(1 + inf) = -0 is the right limit)
-__device__ __forceinline__ float2 silu2(float2 v) {
-  const float2 q = __fmul2_rn(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-  float2 e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(q.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(q.y));
-  e = __fadd2_rn(e, make_float2(1.0f, 1.0f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
-  return __fmul2_rn(v, r);
-}
 __host__ __device__ constexpr int pos_mod(int a, int m) { return ((a % m) + m) % m; }
 __host__ __device__ constexpr int floor_div(int a, int m) { return (a - pos_mod(a, m)) / m; }
 
@@ -916,6 +925,20 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
   float* pooled = reinterpret_cast<float*>(p);
   const int nb = (int)h->cfg.size();
   int rc;
+  // AVEXK_DEBUG_SYNC=1 (bring-up aid): synchronise after every launch and name the launch that failed or never returned
+  static const int dbg_sync = [] { const char* e = getenv("AVEXK_DEBUG_SYNC"); return e ? atoi(e) : 0; }();
+  auto dbg = [&](const char* what, int layer) -> int {
+    if (!dbg_sync) return AVEXK_OK;
+    fprintf(stderr, "[avexk] effnet layer %d %s ...", layer, what);
+    fflush(stderr);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, " %s\n", e == cudaSuccess ? "ok" : cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      set_error("effnet layer %d %s: %s", layer, what, cudaGetErrorString(e));
+      return AVEXK_ECUDA;
+    }
+    return AVEXK_OK;
+  };
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
   auto to_nchw = [&](const float* src, int P, int C, float* dst) -> int {
     dim3 grid(ceil_div(P, 32), ceil_div(C, 32), B);
@@ -939,11 +962,13 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
     const __nv_bfloat16* dw_in = act;
     if (b.expand_w != nullptr) {
       TRY(conv1x1_any(act, b.expand_w, (int)M, c.cexp, c.cin, b.expand_scale, b.expand_shift, 1, nullptr, nullptr, 0, nullptr, ex, 1, st));
+      TRY(dbg("expand", i));
       dw_in = ex;
     }
     const int Ho = conv_out(H, c.kernel, c.stride), Wo = conv_out(W, c.kernel, c.stride);
     AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(unsigned long long) * (size_t)B * c.cexp, st));
     TRY(launch_dwconv(dw_in, B, H, W, c.cexp, c.kernel, c.stride, b.dw_w, b.dw_scale, b.dw_shift, dw, se_sum, st));
+    TRY(dbg("depthwise", i));
     se_mlp_kernel<<<B, 256, (c.cexp + c.csq) * sizeof(float), st>>>(se_sum, 1.0f / (float)(Ho * Wo), c.cexp, c.csq, b.se1_w, b.se1_b,
                                                                     b.se2_w, b.se2_b, se_scale);
     AVEXK_LAUNCH_CHECK();
@@ -953,6 +978,7 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
     // project conv; the squeeze-excitation rescale of its input rides on the A operand (or runs in place first on the hook path)
     TRY(conv1x1_any(dw, b.proj_w, (int)Mo, c.cout, c.cexp, b.proj_scale, b.proj_shift, 0, use_res ? act : nullptr, se_scale, Ho * Wo,
                     hook ? raw : nullptr, act2, 1, st));
+    TRY(dbg("project", i));
     if (hook) TRY(to_nchw(raw, Ho * Wo, c.cout, hook));
     std::swap(act, act2);
     H = Ho;

@@ -55,7 +55,9 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-register 32-point DIF FFT; output index k2 ends up bit-reversed: z[bitrev5(k2)] = X[k2]
+// in-register 32-point DIF FFT on packed complex values (x = re, y = im): a butterfly is two packed adds and, where the twiddle is
+// not trivial, one packed multiply + one packed FMA (d * w = d * c + (-d.y, d.x) * s).  Output index k2 ends up bit-reversed:
+// z[bitrev5(k2)] = X[k2].
 __device__ __forceinline__ void fft32_dif(float2 (&z)[32]) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
@@ -66,13 +68,17 @@ __device__ __forceinline__ void fft32_dif(float2 (&z)[32]) {
         const int j = i | half;
         const int tw = (i & (half - 1)) << s;  // exponent of W32
         const float2 a = z[i], b = z[j];
-        z[i] = make_float2(a.x + b.x, a.y + b.y);
-        const float2 d = make_float2(a.x - b.x, a.y - b.y);
+        z[i] = __fadd2_rn(a, b);
+        const float2 d = __fadd2_rn(a, make_float2(-b.x, -b.y));
         // W32^tw = exp(-2 pi i tw / 32): immediates after unrolling
         constexpr float kCos[16] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f, 7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f, 6.123233996e-17f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
         constexpr float kSin[16] = {-0.000000000e+00f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f, -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f, -1.000000000e+00f, -9.807852804e-01f, -9.238795325e-01f, -8.314696123e-01f, -7.071067812e-01f, -5.555702330e-01f, -3.826834324e-01f, -1.950903220e-01f};
-        const float c = kCos[tw], sn = kSin[tw];
-        z[j] = make_float2(d.x * c - d.y * sn, d.x * sn + d.y * c);
+        if (tw == 0) z[j] = d;
+        else if (tw == 8) z[j] = make_float2(d.y, -d.x);  // * (-i)
+        else {
+          const float c = kCos[tw], sn = kSin[tw];
+          z[j] = __ffma2_rn(d, make_float2(c, c), __fmul2_rn(make_float2(-d.y, d.x), make_float2(sn, sn)));
+        }
       }
     }
   }
@@ -103,29 +109,50 @@ melspec_kernel(const float* __restrict__ wav, long long wav_stride, int T, int f
   if (tid < N1) sw25[tid] = tb.w25[tid];
   __syncthreads();
 
-  // ---- stage 1: thread (f, n2): Y[k1] = W800^(n2 k1) * sum_n1 w[32 n1 + n2] x[f*160 + 32 n1 + n2] W25^(n1 k1) ----
-  // The 25-point DFT of a REAL sequence: only k1 = 0..12 are computed (Y[25 - k1] = conj Y[k1]), both loops fully unrolled so that
-  // every W25 power is an immediate operand -- 650 FFMAs per thread and no loads or index arithmetic (the first version's
-  // table-driven double loop spent 3750 instructions on the same sums).
+  // ---- stage 1: thread (k1 half, frame pair, n2): Y[k1] = W800^(n2 k1) * sum_n1 w[32 n1 + n2] x[f*160 + 32 n1 + n2] W25^(n1 k1) ----
+  // The 25-point DFT of a REAL sequence, brute force with every W25 power an immediate operand, for TWO frames at once: the
+  // two frames' samples ride in one packed fp32x2 register pair and share the immediate.  Real input: only k1 = 0..12 are
+  // computed (Y[25 - k1] = conj Y[k1]), and the sums run over a[n] = x[n] + x[25-n] (cosine part) and b[n] = x[n] - x[25-n]
+  // (sine part), n = 1..12: 24 packed FMAs per k1 and frame pair instead of the 100 scalar FMAs of the plain double loop.
+  // The two halves of the CTA split the k1 range (0..6 | 7..12).
   {
     constexpr float kC25[25] = {1.000000000e+00f, 9.685831611e-01f, 8.763066800e-01f, 7.289686274e-01f, 5.358267950e-01f, 3.090169944e-01f, 6.279051953e-02f, -1.873813146e-01f, -4.257792916e-01f, -6.374239897e-01f, -8.090169944e-01f, -9.297764859e-01f, -9.921147013e-01f, -9.921147013e-01f, -9.297764859e-01f, -8.090169944e-01f, -6.374239897e-01f, -4.257792916e-01f, -1.873813146e-01f, 6.279051953e-02f, 3.090169944e-01f, 5.358267950e-01f, 7.289686274e-01f, 8.763066800e-01f, 9.685831611e-01f};
     constexpr float kS25[25] = {-0.000000000e+00f, -2.486898872e-01f, -4.817536741e-01f, -6.845471059e-01f, -8.443279255e-01f, -9.510565163e-01f, -9.980267284e-01f, -9.822872507e-01f, -9.048270525e-01f, -7.705132428e-01f, -5.877852523e-01f, -3.681245527e-01f, -1.253332336e-01f, 1.253332336e-01f, 3.681245527e-01f, 5.877852523e-01f, 7.705132428e-01f, 9.048270525e-01f, 9.822872507e-01f, 9.980267284e-01f, 9.510565163e-01f, 8.443279255e-01f, 6.845471059e-01f, 4.817536741e-01f, 2.486898872e-01f};
-    const int f = tid >> 5, n2 = tid & 31;
-    float xv[N1];
+    const int hh = tid >> 7, pr = (tid >> 5) & 3, n2 = tid & 31;
+    const float* xa = sx + (2 * pr) * HOP + n2;
+    float2 x0, av[12], bv[12];  // (frame 2 pr, frame 2 pr + 1)
+    {
+      const float w0 = __ldg(tb.window + n2);
+      x0 = make_float2(xa[0] * w0, xa[HOP] * w0);
+    }
 #pragma unroll
-    for (int n1 = 0; n1 < N1; ++n1) xv[n1] = sx[f * HOP + 32 * n1 + n2] * __ldg(tb.window + 32 * n1 + n2);
-    float2* dst = sy + (f * N2 + n2) * N1;
+    for (int n = 1; n <= 12; ++n) {
+      const float wl = __ldg(tb.window + 32 * n + n2), wh = __ldg(tb.window + 32 * (N1 - n) + n2);
+      const float2 lo = make_float2(xa[32 * n] * wl, xa[HOP + 32 * n] * wl);
+      const float2 hi = make_float2(xa[32 * (N1 - n)] * wh, xa[HOP + 32 * (N1 - n)] * wh);
+      av[n - 1] = __fadd2_rn(lo, hi);
+      bv[n - 1] = __fadd2_rn(lo, make_float2(-hi.x, -hi.y));
+    }
+    float2* dst0 = sy + ((2 * pr) * N2 + n2) * N1;  // frame 2 pr; frame 2 pr + 1 is N2 * N1 further
     const float2* tw = tb.w800 + n2 * N1;
+    auto emit = [&](int k1, float2 re, float2 im) {  // Y[k1] = re + i im for both frames -> twiddle -> shared memory
+      const float2 t = __ldg(tw + k1);
+      const float2 yr = __ffma2_rn(re, make_float2(t.x, t.x), __fmul2_rn(im, make_float2(-t.y, -t.y)));
+      const float2 yi = __ffma2_rn(re, make_float2(t.y, t.y), __fmul2_rn(im, make_float2(t.x, t.x)));
+      dst0[k1] = make_float2(yr.x, yi.x);
+      dst0[N2 * N1 + k1] = make_float2(yr.y, yi.y);
+    };
 #pragma unroll
     for (int k1 = 0; k1 <= N1 / 2; ++k1) {
-      float re = 0.f, im = 0.f;
+      if ((k1 <= 6) != (hh == 0)) continue;  // (CTA-half uniform)
+      float2 re = x0, im = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int n1 = 0; n1 < N1; ++n1) {
-        re = fmaf(xv[n1], kC25[(n1 * k1) % N1], re);
-        im = fmaf(xv[n1], kS25[(n1 * k1) % N1], im);
+      for (int n = 1; n <= 12; ++n) {
+        re = __ffma2_rn(av[n - 1], make_float2(kC25[(n * k1) % N1], kC25[(n * k1) % N1]), re);
+        if (k1 > 0) im = __ffma2_rn(bv[n - 1], make_float2(kS25[(n * k1) % N1], kS25[(n * k1) % N1]), im);
       }
-      dst[k1] = cmul(make_float2(re, im), __ldg(tw + k1));
-      if (k1 > 0) dst[N1 - k1] = cmul(make_float2(re, -im), __ldg(tw + N1 - k1));
+      emit(k1, re, im);
+      if (k1 > 0) emit(N1 - k1, re, make_float2(-im.x, -im.y));
     }
   }
   __syncthreads();

@@ -11,10 +11,10 @@
 //     in flight; W stays resident in shared memory when it fits (every layer of the high-resolution stages);
 //   * one MMA thread issues kind::f16 UMMAs (M = 128, N = the layer's N rounded to 16) into a ring of up to eight TMEM
 //     accumulators, so the epilogue of tile t overlaps the loads and MMAs of tiles t+1 .. t+7;
-//   * eight epilogue warps (two per TMEM lane quarter) read 8-column chunks, apply BatchNorm / SiLU / residual with packed
-//     fp32x2 arithmetic, and park the fp16 row in a padded shared-memory tile; each row then leaves with ONE bulk copy
-//     (cp.async.bulk shared -> global): full-line writes, no per-thread scattered stores;
-//   * squeeze-excitation: four "scaler" warps multiply the A tile by the clip's channel scale in shared memory before the
+//   * eight or twelve epilogue warps (two or three per TMEM lane quarter, taking tiles in turn) each own 32 full rows of a
+//     tile: BatchNorm / SiLU / residual with packed fp32x2 arithmetic, fp16 into the warp's swizzled staging boxes, one TMA
+//     tensor store per [32 x 64] box: full-line writes, no barrier among the epilogue warps;
+//   * squeeze-excitation: eight "scaler" warps multiply the A tile by the clip's channel scale in shared memory before the
 //     MMA reads it -- the separate read-modify-write pass over the depthwise output (se_apply_kernel) disappears.
 #include "common.cuh"
 #include "kernels.cuh"
@@ -26,8 +26,8 @@ namespace {
 
 constexpr int PW_BM = 128, PW_BK = 64, PW_A_BYTES = PW_BM * PW_BK * 2;
 constexpr int PW_MAX_STAGES = 8, PW_MAX_ACC = 8;
-constexpr int PW_WARP_LOAD = 0, PW_WARP_MMA = 1, PW_WARP_SCALE0 = 2, PW_WARP_EPI0 = 6, PW_THREADS = 14 * 32;
-constexpr int PW_EPI_THREADS = 256;
+constexpr int PW_BOX_BYTES = 32 * 128;  // one store box: 32 rows x 64 fp16 columns
+constexpr int PW_WARP_LOAD = 0, PW_WARP_MMA = 1, PW_WARP_SCALE0 = 2, PW_WARP_SE_EPI0 = 10, PW_THREADS = 14 * 32;
 
 struct PwArgs {
   int M, N, K;
@@ -36,7 +36,7 @@ struct PwArgs {
   int stages, stage_bytes; // ring depth; bytes per stage (A block, + W block when W is streamed)
   int w_resident, w_block_bytes;
   int acc_stride, acc_stages;
-  int ob_pitch;            // bytes per row of the output staging tile (ntb * 2 + 16: conflict-free 16-byte row writes)
+  int direct;              // rows under 64 columns: plain 16-byte stores instead of staged TMA stores
   int off_w, off_ob, off_tab, off_bar;
   uint32_t idesc;
   int m_tiles, silu, hw;
@@ -45,14 +45,14 @@ struct PwArgs {
   __nv_bfloat16* out;
 };
 
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
@@ -80,7 +80,8 @@ __device__ __forceinline__ float2 pw_silu2(float2 v) {
 }
 
 __global__ void __launch_bounds__(PW_THREADS, 1)
-pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const PwArgs g) {
+pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                 const __grid_constant__ CUtensorMap map_out, const PwArgs g) {
   extern __shared__ unsigned char pw_smem_raw[];
   unsigned char* smem = pw_smem_raw + ((1024u - (ptx::smem_u32(pw_smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_a = ptx::smem_u32(smem);
@@ -101,14 +102,15 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_w);
+    ptx::prefetch_tensormap(&map_out);
     for (int s = 0; s < g.stages; ++s) {
       ptx::mbar_init(&a_full[s], 1);
-      ptx::mbar_init(&a_ready[s], 4);
+      ptx::mbar_init(&a_ready[s], PW_WARP_SE_EPI0 - PW_WARP_SCALE0);  // one arrival per scaler warp
       ptx::mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < g.acc_stages; ++s) {
       ptx::mbar_init(&t_full[s], 1);
-      ptx::mbar_init(&t_empty[s], PW_EPI_THREADS / 32);
+      ptx::mbar_init(&t_empty[s], 4);  // one warp per TMEM lane quarter
     }
     ptx::mbar_init(w_full, 1);
     ptx::fence_barrier_init();
@@ -175,61 +177,111 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == g.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < PW_WARP_EPI0) {
+  } else if (se && warp < PW_WARP_SE_EPI0) {
     // ===================== squeeze-excitation scalers: A[row, :] *= se[clip(row), :] in shared memory =====================
-    if (se) {
-      const int row = threadIdx.x - PW_WARP_SCALE0 * 32;  // 0..127: one A row per thread
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mt = tile / g.n_nt, grow = mt * PW_BM + row;
-        const float* sp = g.se_scale + (size_t)(grow < g.M ? grow / g.hw : 0) * g.K;
-        for (int kb = 0; kb < g.kblocks; ++kb) {
-          ptx::mbar_wait(&a_full[stage], phase);
-          if (grow < g.M) {
-            const uint32_t rowa = smem_a + stage * g.stage_bytes + row * 128;
+    // Eight warps, two threads per A row (four 16-byte chunks each).  The clip's scale values are fetched BEFORE the wait on
+    // the stage (they depend only on the tile), and a thread's chunks are read together, so a stage costs one shared-memory
+    // round trip, not a chain of dependent global loads.  The clip index advances incrementally (no division per tile).
+    const int t = threadIdx.x - PW_WARP_SCALE0 * 32, row = t >> 1, hsel = t & 1;  // row 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const int step_rows = gridDim.x * PW_BM, dq = step_rows / g.hw, dr = step_rows - dq * g.hw;
+    int last_mt = blockIdx.x / g.n_nt;
+    int grow = last_mt * PW_BM + row, clip = grow / g.hw, rem = grow - clip * g.hw;
+    uint32_t joff[4];
+    int jcol[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int j = (i + row) & 7;                       // rotate: the 8 lanes of a quarter-warp hit 8 bank groups
-              const int col = kb * PW_BK + ((j ^ (row & 7)) << 3);  // logical k of this 16-byte chunk (128-byte swizzle)
-              if (col < g.K) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp + col)), s1 = __ldg(reinterpret_cast<const float4*>(sp + col + 4));
-                uint4 v = lds128u(rowa + j * 16);
-                float2 a = unpack_h16(v.x), b = unpack_h16(v.y), c = unpack_h16(v.z), d = unpack_h16(v.w);
-                v.x = pack_h16(a.x * s0.x, a.y * s0.y);
-                v.y = pack_h16(b.x * s0.z, b.y * s0.w);
-                v.z = pack_h16(c.x * s1.x, c.y * s1.y);
-                v.w = pack_h16(d.x * s1.z, d.y * s1.w);
-                sts128u(rowa + j * 16, v);
-              }
+    for (int i = 0; i < 4; ++i) {
+      const int j = (4 * hsel + i + row) & 7;  // the 8 lanes of a quarter-warp (4 rows x 2 halves) hit 8 distinct bank groups
+      joff[i] = row * 128 + j * 16;
+      jcol[i] = (j ^ (row & 7)) << 3;          // logical k (inside the k-block) of that chunk under the 128-byte swizzle
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int mt = tile / g.n_nt;
+      if (mt != last_mt) {  // this thread's row moved: one N tile per row block -> by exactly one grid stride, no division
+        if (g.n_nt == 1) {
+          clip += dq; rem += dr;
+          if (rem >= g.hw) { rem -= g.hw; ++clip; }
+          grow += step_rows;
+        } else {
+          grow = mt * PW_BM + row;
+          clip = grow / g.hw;
+          rem = grow - clip * g.hw;
+        }
+        last_mt = mt;
+      }
+      const float* sp = g.se_scale + (size_t)(grow < g.M ? clip : 0) * g.K;
+      for (int kb = 0; kb < g.kblocks; ++kb) {
+        float4 s0[4], s1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = kb * PW_BK + jcol[i];
+          if (col < g.K) {
+            s0[i] = __ldg(reinterpret_cast<const float4*>(sp + col));
+            s1[i] = __ldg(reinterpret_cast<const float4*>(sp + col + 4));
+          }
+        }
+        ptx::mbar_wait(&a_full[stage], phase);
+        if (grow < g.M) {
+          const uint32_t base = smem_a + stage * g.stage_bytes;
+          uint4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (kb * PW_BK + jcol[i] < g.K) v[i] = lds128u(base + joff[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (kb * PW_BK + jcol[i] < g.K) {
+              const float2 a = unpack_h16(v[i].x), b = unpack_h16(v[i].y), c = unpack_h16(v[i].z), d = unpack_h16(v[i].w);
+              uint4 o;
+              o.x = pack_h16(a.x * s0[i].x, a.y * s0[i].y);
+              o.y = pack_h16(b.x * s0[i].z, b.y * s0[i].w);
+              o.z = pack_h16(c.x * s1[i].x, c.y * s1[i].y);
+              o.w = pack_h16(d.x * s1[i].z, d.y * s1[i].w);
+              sts128u(base + joff[i], o);
             }
           }
-          ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (8 warps: TMEM lane quarter x column half) =====================
-    const int ew = warp - PW_WARP_EPI0, quarter = warp & 3, half = ew >> 2;
+    // ===================== epilogue =====================
+    // Warps 10..13 (squeeze-excitation mode: the project convolutions have narrow, activation-free outputs) or 2..13: `ne` = 1 or
+    // 3 warps per TMEM lane quarter, which take the CTA's tiles in turn.  A warp owns 32 FULL rows of its tile from TMEM to global memory, so there is no barrier among epilogue warps:
+    // 16-column chunks (double-buffered TMEM loads) -> BatchNorm / SiLU / residual in packed fp32x2 -> fp16 into this warp's
+    // staging boxes ([32 rows x 64 columns], 128-byte swizzle: conflict-free 16-byte writes) -> one TMA tensor store per
+    // box, issued by lane 0 (full-line writes; the map clips columns >= N and rows >= M).  Rows narrower than 64 columns go
+    // out with plain 16-byte stores instead (the warp's 32 rows are one contiguous range of global memory either way).
+    // ne <= accumulator stages: a warp waits on t_full[acc] by phase PARITY, which only tells the current phase from the previous
+    // one -- the previous use of the accumulator (tile it - acc_stages) must be complete when the warp, done with tile it - ne,
+    // starts waiting for tile it.  (With three warps on two accumulators a warp would take tile it - 4's completion for tile it's.)
+    const int first = se ? PW_WARP_SE_EPI0 : PW_WARP_SCALE0, ne = se ? 1 : (g.acc_stages < 3 ? g.acc_stages : 3);
+    const int quarter = warp & 3, sub = (warp - first) >> 2;
     const int row = quarter * 32 + lane;
-    const int half_cols = g.ntb >> 1, nch = half_cols >> 3;  // 8-column chunks per thread and tile
+    const int nch = g.ntb >> 4;  // 16-column chunks per tile
     const uint32_t tab_a = smem_a + g.off_tab;
-    int acc = 0, par = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+    const bool direct = g.direct != 0;
+    const uint32_t stg = smem_a + g.off_ob + (warp - PW_WARP_SCALE0) * (2 * PW_BOX_BYTES);  // this warp's two staging boxes
+    const uint32_t sw = lane & 7;
+    int it = 0;
+    uint32_t box_par = 0;  // staging box in use (alternates per 64-column box)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      if (it % ne != sub) continue;  // (a warp with sub >= ne has no tiles)
+      const int acc = it % g.acc_stages;
+      const uint32_t acc_phase = (it / g.acc_stages) & 1;
       const int mt = tile / g.n_nt, nt = tile - mt * g.n_nt;
-      const int grow = mt * PW_BM + row, n0 = nt * g.ntb + half * half_cols;
-      const uint32_t ob_row = smem_a + g.off_ob + par * (PW_BM * g.ob_pitch) + row * g.ob_pitch + half * half_cols * 2;
+      const int grow = mt * PW_BM + row, n0 = nt * g.ntb;
       const __nv_bfloat16* resp = g.res != nullptr && grow < g.M ? g.res + (size_t)grow * g.N + n0 : nullptr;
+      __nv_bfloat16* outp = g.out + (size_t)grow * g.N + n0;
       ptx::mbar_wait(&t_full[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * g.acc_stride + half * half_cols;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * g.acc_stride;
 
-      auto process = [&](const uint32_t (&v)[8], int i) {
-        const int col = n0 + i * 8;
+      auto process8 = [&](const uint32_t* v, int c8) {  // 8 columns starting at tile column c8 * 8
+        const int col = n0 + c8 * 8;
         if (col >= g.N) return;  // (warp-uniform) zero-padded columns of the last N tile
         const float4 sc0 = lds128f(tab_a + col * 4), sc1 = lds128f(tab_a + col * 4 + 16);
         const float4 sh0 = lds128f(tab_a + (g.N + col) * 4), sh1 = lds128f(tab_a + (g.N + col) * 4 + 16);
@@ -241,49 +293,54 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           y0 = pw_silu2(y0); y1 = pw_silu2(y1); y2 = pw_silu2(y2); y3 = pw_silu2(y3);
         }
         if (resp != nullptr) {
-          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + i * 8));
+          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + c8 * 8));
           y0 = __fadd2_rn(y0, unpack_h16(rv.x)); y1 = __fadd2_rn(y1, unpack_h16(rv.y));
           y2 = __fadd2_rn(y2, unpack_h16(rv.z)); y3 = __fadd2_rn(y3, unpack_h16(rv.w));
         }
-        sts128u(ob_row + i * 16, make_uint4(pack_h16(y0.x, y0.y), pack_h16(y1.x, y1.y), pack_h16(y2.x, y2.y), pack_h16(y3.x, y3.y)));
+        const uint4 pk = make_uint4(pack_h16(y0.x, y0.y), pack_h16(y1.x, y1.y), pack_h16(y2.x, y2.y), pack_h16(y3.x, y3.y));
+        if (!direct) sts128u(stg + box_par * PW_BOX_BYTES + lane * 128 + (((c8 & 7) ^ sw) << 4), pk);
+        else if (grow < g.M) *reinterpret_cast<uint4*>(outp + c8 * 8) = pk;
+      };
+      // one 16-column chunk; a 64-column box is four chunks: before its first chunk the box written two boxes ago must have left
+      // the staging buffer, after its last chunk (or the tile's last) lane 0 hands it to the TMA engine
+      auto chunk = [&](const uint32_t* v, int i) {
+        if (!direct && (i & 3) == 0) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        process8(v, 2 * i);
+        process8(v + 8, 2 * i + 1);
+        if (!direct && ((i & 3) == 3 || i == nch - 1)) {
+          ptx::fence_proxy_async();  // the warp's shared-memory writes -> visible to the TMA store
+          __syncwarp();
+          const int c0 = n0 + (i >> 2) * 64;
+          if (lane == 0 && c0 < g.N) ptx::tma_store_2d_s(&map_out, stg + box_par * PW_BOX_BYTES, c0, mt * PW_BM + quarter * 32);
+          if (lane == 0) ptx::tma_store_commit();  // (possibly empty: keeps one group per box for the wait above)
+          box_par ^= 1;
+        }
+      };
+      auto release = [&]() {  // every TMEM read of this accumulator has completed: hand it back to the MMA thread
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
       };
 
-      uint32_t va[8], vb[8];
-      tmem_ld_32x8(t_addr, va);
+      uint32_t va[16], vb[16];
+      tmem_ld_32x16(t_addr, va);
       for (int i = 0; i < nch; i += 2) {
         ptx::tmem_ld_wait();
-        if (i + 1 < nch) tmem_ld_32x8(t_addr + (i + 1) * 8, vb);
-        else {  // every TMEM read of this accumulator has completed: hand it back to the MMA thread before the last chunk's math
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-        }
-        process(va, i);
+        if (i + 1 < nch) tmem_ld_32x16(t_addr + (i + 1) * 16, vb);
+        else release();
+        chunk(va, i);
         if (i + 1 < nch) {
           ptx::tmem_ld_wait();
-          if (i + 2 < nch) tmem_ld_32x8(t_addr + (i + 2) * 8, va);
-          else {
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
-          }
-          process(vb, i + 1);
+          if (i + 2 < nch) tmem_ld_32x16(t_addr + (i + 2) * 16, va);
+          else release();
+          chunk(vb, i + 1);
         }
       }
-      if (++acc == g.acc_stages) { acc = 0; acc_phase ^= 1; }
-
-      // the tile is parked in shared memory: one bulk copy per row (issued by the row's half-0 thread).  The staging buffer
-      // of the PREVIOUS tile is free once that thread's earlier copy has finished reading -- checked before the barrier.
-      ptx::fence_proxy_async();
-      if (half == 0) ptx::tma_store_wait_read();
-      ptx::named_bar_sync(1, PW_EPI_THREADS);
-      if (half == 0 && grow < g.M) {
-        const int nvalid = min(g.ntb, g.N - nt * g.ntb);
-        bulk_store(g.out + (size_t)grow * g.N + nt * g.ntb, ob_row, nvalid * 2);
-        ptx::tma_store_commit();
-      }
     }
-    if (half == 0) ptx::tma_store_wait_all();  // the copies must have been performed before the CTA exits
+    if (!direct && lane == 0) ptx::tma_store_wait_all();  // the stores must have been performed before the CTA exits
   }
 
   ptx::tc_fence_before();
@@ -309,19 +366,22 @@ int pointwise_launch(const void* A, const void* W, int M, int N, int K, const fl
   PwArgs g{};
   g.M = M; g.N = N; g.K = K;
   g.kblocks = ceil_div(K, PW_BK);
-  // N tiling: one tile when N <= 256, else the fewest tiles of <= 160 columns (keeps three 36 KB stages + two staging tiles)
+  // N tiling: one tile when N <= 256, else 128-column tiles (a multiple of the 64-column store box: a box never spills into the
+  // next tile's columns)
   const int n16 = (N + 15) / 16 * 16;
   if (n16 <= 256) { g.n_nt = 1; g.ntb = n16; }
-  else { g.n_nt = ceil_div(N, 160); g.ntb = (ceil_div(N, g.n_nt) + 15) / 16 * 16; }
+  else { g.ntb = 128; g.n_nt = ceil_div(N, 128); }
   g.w_block_bytes = g.ntb * 128;
-  g.ob_pitch = g.ntb * 2 + 16;
-  const int ob_bytes = 2 * PW_BM * g.ob_pitch, tab_bytes = (2 * N * 4 + 15) / 16 * 16;
+  const int tab_bytes = (2 * N * 4 + 15) / 16 * 16;
   const int bar_bytes = (3 * PW_MAX_STAGES + 2 * PW_MAX_ACC + 1) * 8 + 16;
-  const int budget = 227 * 1024 - 1024 - ob_bytes - tab_bytes - bar_bytes - 128;
   const int w_all = g.kblocks * g.w_block_bytes;
-  g.w_resident = g.n_nt == 1 && budget - w_all >= 4 * PW_A_BYTES;
+  g.direct = g.ntb < 64;
+  const int ob_bytes = g.direct ? 0 : 12 * 2 * PW_BOX_BYTES;  // two staging boxes per epilogue warp
+  // shared-memory plan: staging boxes, W resident when it fits beside >= 4 stages, the rest to the load ring
+  const int avail = 227 * 1024 - 1024 - tab_bytes - bar_bytes - 128 - ob_bytes;
+  g.w_resident = g.n_nt == 1 && avail - w_all >= 4 * PW_A_BYTES;
   g.stage_bytes = PW_A_BYTES + (g.w_resident ? 0 : g.w_block_bytes);
-  int stages = (budget - (g.w_resident ? w_all : 0)) / g.stage_bytes;
+  int stages = (avail - (g.w_resident ? w_all : 0)) / g.stage_bytes;
   AVEXK_CHECK_ARG(stages >= 2, "pointwise: tile does not fit shared memory (N=%d K=%d)", N, K);
   g.stages = stages > PW_MAX_STAGES ? PW_MAX_STAGES : stages;
   g.off_w = g.stages * g.stage_bytes;
@@ -335,10 +395,12 @@ int pointwise_launch(const void* A, const void* W, int M, int N, int K, const fl
   g.silu = silu; g.hw = hw;
   g.scale = scale; g.shift = shift; g.se_scale = se_scale; g.res = res;
   g.out = reinterpret_cast<__nv_bfloat16*>(out);
-  CUtensorMap map_a, map_w;
+  CUtensorMap map_a, map_w, map_out;
   int rc = make_tmap_2d_bf16(&map_a, A, M, K, K, PW_BM, PW_BK);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&map_w, W, N, K, K, g.ntb, PW_BK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&map_out, out, M, N, N, 32, 64);  // store boxes: 32 rows x 64 columns, 128-byte swizzle
   if (rc) return rc;
   const size_t smem = 1024 + (size_t)g.off_bar + bar_bytes;
   static bool attr_set[64] = {};
@@ -349,7 +411,7 @@ int pointwise_launch(const void* A, const void* W, int M, int N, int K, const fl
   }
   const int tiles = g.m_tiles * g.n_nt;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  pointwise_kernel<<<grid, PW_THREADS, smem, st>>>(map_a, map_w, g);
+  pointwise_kernel<<<grid, PW_THREADS, smem, st>>>(map_a, map_w, map_out, g);
   AVEXK_LAUNCH_CHECK();
   return AVEXK_OK;
 }

@@ -97,7 +97,8 @@ def test_conv1x1(lib, M, N, K, silu, res):
 # the MBConv shapes of the 5 s bench (rows = a few 128-row tiles + a ragged tail), project convs with the SE scale fused
 @pytest.mark.parametrize("rows_per_clip,clips,N,K,res", [(16000, 2, 16, 32, False), (4000, 3, 24, 96, False), (1008, 5, 40, 144, False),
                                                          (1008, 5, 40, 240, True), (256, 9, 80, 480, True), (256, 9, 112, 672, True),
-                                                         (64, 37, 192, 1152, True), (64, 37, 320, 1152, False), (100, 3, 24, 144, True)])
+                                                         (64, 37, 192, 1152, True), (64, 37, 320, 1152, False), (100, 3, 24, 144, True),
+                                                         (1008, 60, 40, 240, True), (4000, 20, 24, 96, False)])  # 3-4 tiles per CTA
 def test_conv1x1_se(lib, rows_per_clip, clips, N, K, res):
     g = torch.Generator(device="cuda").manual_seed(N * K)
     M = rows_per_clip * clips
@@ -121,7 +122,9 @@ def test_conv1x1_se(lib, rows_per_clip, clips, N, K, res):
 
 
 @pytest.mark.parametrize("M,N,K,silu", [(128 * 70 + 5, 96, 16, 1), (5000, 144, 24, 1), (3000, 240, 40, 1), (1500, 480, 80, 1),
-                                        (700, 672, 112, 1), (400, 1152, 192, 1), (333, 8, 8, 0), (1, 1280, 320, 1)])
+                                        (700, 672, 112, 1), (400, 1152, 192, 1), (333, 8, 8, 0), (1, 1280, 320, 1),
+                                        # several tiles per CTA: the accumulator ring (2 stages at N = 240, 5 at N = 96) wraps
+                                        (148 * 128 * 3 + 77, 240, 40, 1), (148 * 128 * 6 + 5, 96, 16, 1), (148 * 128 * 2 + 1, 480, 80, 1)])
 def test_conv1x1_wide_and_tiled(lib, M, N, K, silu):
     """expand-conv shapes: N up to 1152 (several N tiles, W streamed), K from one partial k-block to three."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
