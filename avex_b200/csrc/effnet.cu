@@ -665,7 +665,11 @@ int launch_dwconv_tma(const __nv_bfloat16* in, int B, int H, int W, int C, int H
     AVEXK_CUDA(cudaFuncSetAttribute(dwconv_tma_kernel<K, S, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_set[dev] = true;
   }
-  int per_slice = 2 * num_sms() / a.n_cs;  // CTAs per channel slice (two CTAs per SM are resident)
+  // resident CTAs per SM: 128 registers per thread allow 512 threads; shared memory is not the limit at <= 100 KB per CTA
+  int ctas_per_sm = 512 / p.threads;
+  if ((size_t)ctas_per_sm * (smem + 1024) > 220 * 1024) ctas_per_sm = (int)(220 * 1024 / (smem + 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int per_slice = ctas_per_sm * num_sms() / a.n_cs;  // CTAs per channel slice
   if (per_slice < 1) per_slice = 1;
   if (per_slice > a.n_tiles) per_slice = a.n_tiles;
   const int grid = per_slice * a.n_cs;

@@ -11,7 +11,7 @@
 //     in flight; W stays resident in shared memory when it fits (every layer of the high-resolution stages);
 //   * one MMA thread issues kind::f16 UMMAs (M = 128, N = the layer's N rounded to 16) into a ring of up to eight TMEM
 //     accumulators, so the epilogue of tile t overlaps the loads and MMAs of tiles t+1 .. t+7;
-//   * eight or twelve epilogue warps (two or three per TMEM lane quarter, taking tiles in turn) each own 32 full rows of a
+//   * eight or sixteen epilogue warps (two or four per TMEM lane quarter, taking tiles in turn) each own 32 full rows of a
 //     tile: BatchNorm / SiLU / residual with packed fp32x2 arithmetic, fp16 into the warp's swizzled staging boxes, one TMA
 //     tensor store per [32 x 64] box: full-line writes, no barrier among the epilogue warps;
 //   * squeeze-excitation: eight "scaler" warps multiply the A tile by the clip's channel scale in shared memory before the
@@ -27,7 +27,8 @@ namespace {
 constexpr int PW_BM = 128, PW_BK = 64, PW_A_BYTES = PW_BM * PW_BK * 2;
 constexpr int PW_MAX_STAGES = 8, PW_MAX_ACC = 8;
 constexpr int PW_BOX_BYTES = 32 * 128;  // one store box: 32 rows x 64 fp16 columns
-constexpr int PW_WARP_LOAD = 0, PW_WARP_MMA = 1, PW_WARP_SCALE0 = 2, PW_WARP_SE_EPI0 = 10, PW_THREADS = 14 * 32;
+constexpr int PW_WARP_LOAD = 0, PW_WARP_MMA = 1, PW_WARP_SCALE0 = 2, PW_WARP_SE_EPI0 = 10, PW_WARPS = 18, PW_THREADS = PW_WARPS * 32;
+constexpr int PW_EPI_SLOTS = PW_WARPS - PW_WARP_SCALE0;  // warps that may run the epilogue (sixteen without SE, eight with)
 
 struct PwArgs {
   int M, N, K;
@@ -77,6 +78,16 @@ __device__ __forceinline__ float2 pw_silu2(float2 v) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
   return __fmul2_rn(v, r);
+}
+
+// wait with back-off for the two single-thread roles (producer, MMA issuer): their rings are several tiles deep, so a few hundred
+// nanoseconds of wake-up latency cost nothing, while a tight poll loop takes issue slots from the epilogue warps of its sub-core
+__device__ __forceinline__ void pw_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 24)) __trap();
+  }
 }
 
 __global__ void __launch_bounds__(PW_THREADS, 1)
@@ -140,7 +151,7 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int mt = tile / g.n_nt, nt = tile - mt * g.n_nt;
         for (int kb = 0; kb < g.kblocks; ++kb) {
-          ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+          pw_wait_relaxed(&a_empty[stage], phase ^ 1);
           unsigned char* dst = smem + stage * g.stage_bytes;
           ptx::mbar_arrive_expect_tx(&a_full[stage], g.stage_bytes);
           ptx::tma_load_2d(dst, &map_a, &a_full[stage], kb * PW_BK, mt * PW_BM);
@@ -159,11 +170,11 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&t_empty[acc], acc_phase ^ 1);
+        pw_wait_relaxed(&t_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * g.acc_stride;
         for (int kb = 0; kb < g.kblocks; ++kb) {
-          ptx::mbar_wait(se ? &a_ready[stage] : &a_full[stage], phase);
+          pw_wait_relaxed(se ? &a_ready[stage] : &a_full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = smem_a + stage * g.stage_bytes;
           const uint32_t sb = g.w_resident ? smem_a + g.off_w + kb * g.w_block_bytes : sa + PW_A_BYTES;
@@ -249,8 +260,8 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ===================== epilogue =====================
-    // Warps 10..13 (squeeze-excitation mode: the project convolutions have narrow, activation-free outputs) or 2..13: `ne` = 1 or
-    // 3 warps per TMEM lane quarter, which take the CTA's tiles in turn.  A warp owns 32 FULL rows of its tile from TMEM to global memory, so there is no barrier among epilogue warps:
+    // Warps 10..17 (squeeze-excitation mode) or 2..17: `ne` = up to 2 or 4 warps per TMEM lane quarter, which take the CTA's tiles
+    // in turn (the SiLU epilogue is special-function-unit bound: it wants every warp the register file can hold).  A warp owns 32 FULL rows of its tile from TMEM to global memory, so there is no barrier among epilogue warps:
     // 16-column chunks (double-buffered TMEM loads) -> BatchNorm / SiLU / residual in packed fp32x2 -> fp16 into this warp's
     // staging boxes ([32 rows x 64 columns], 128-byte swizzle: conflict-free 16-byte writes) -> one TMA tensor store per
     // box, issued by lane 0 (full-line writes; the map clips columns >= N and rows >= M).  Rows narrower than 64 columns go
@@ -258,7 +269,7 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ne <= accumulator stages: a warp waits on t_full[acc] by phase PARITY, which only tells the current phase from the previous
     // one -- the previous use of the accumulator (tile it - acc_stages) must be complete when the warp, done with tile it - ne,
     // starts waiting for tile it.  (With three warps on two accumulators a warp would take tile it - 4's completion for tile it's.)
-    const int first = se ? PW_WARP_SE_EPI0 : PW_WARP_SCALE0, ne = se ? 1 : (g.acc_stages < 3 ? g.acc_stages : 3);
+    const int first = se ? PW_WARP_SE_EPI0 : PW_WARP_SCALE0, ne_max = se ? 2 : 4, ne = g.acc_stages < ne_max ? g.acc_stages : ne_max;
     const int quarter = warp & 3, sub = (warp - first) >> 2;
     const int row = quarter * 32 + lane;
     const int nch = g.ntb >> 4;  // 16-column chunks per tile
@@ -376,7 +387,7 @@ int pointwise_launch(const void* A, const void* W, int M, int N, int K, const fl
   const int bar_bytes = (3 * PW_MAX_STAGES + 2 * PW_MAX_ACC + 1) * 8 + 16;
   const int w_all = g.kblocks * g.w_block_bytes;
   g.direct = g.ntb < 64;
-  const int ob_bytes = g.direct ? 0 : 12 * 2 * PW_BOX_BYTES;  // two staging boxes per epilogue warp
+  const int ob_bytes = g.direct ? 0 : PW_EPI_SLOTS * 2 * PW_BOX_BYTES;  // two staging boxes per epilogue warp
   // shared-memory plan: staging boxes, W resident when it fits beside >= 4 stages, the rest to the load ring
   const int avail = 227 * 1024 - 1024 - tab_bytes - bar_bytes - 128 - ob_bytes;
   g.w_resident = g.n_nt == 1 && avail - w_all >= 4 * PW_A_BYTES;
