@@ -322,8 +322,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
   const uint32_t ring_a = ptx::smem_u32(smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a.ring * a.slot_bytes);  // full[ring], empty[ring]
   const uint32_t full_a = ptx::smem_u32(bars), empty_a = full_a + DW_MAX_RING * 8;
-  unsigned long long* sse = reinterpret_cast<unsigned long long*>(bars + 2 * DW_MAX_RING);  // [2][csl], 40.24 fixed point
-  const int n_cons_warps = blockDim.x / 32 - 1, n_cons = n_cons_warps * 32;
+  const int n_cons_warps = blockDim.x / 32 - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&map_in);
@@ -333,7 +332,6 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
     }
     ptx::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 2 * a.csl; i += blockDim.x) sse[i] = 0ull;
   __syncthreads();
 
   if (warp == n_cons_warps) {
@@ -349,7 +347,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
         for (int r = 0; r < nsteps; ++r) {
           const int hi = hi0 + r;
           if ((unsigned)hi >= (unsigned)a.H) continue;  // a padding row: the consumers know, nothing is sent
-          ptx::mbar_wait_a(empty_a + slot * 8, phase ^ 1);
+          while (!ptx::mbar_try_wait_a(empty_a + slot * 8, phase ^ 1)) __nanosleep(64);  // (back-off: the ring is rows deep)
           ptx::mbar_arrive_expect_tx_a(full_a + slot * 8, a.row_bytes);
           ptx::tma_load_4d_a(ring_a + slot * a.slot_bytes, &map_in, full_a + slot * 8, cs * a.csl, wi0, hi, t.b);
           if (++slot == a.ring) { slot = 0; phase ^= 1; }
@@ -365,7 +363,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
   const int cvv = active ? tid % a.pv : 0, cg = active ? tid / a.pv : 0;  // idle threads shadow thread 0 (no stores)
   const uint32_t x_off = ((cg * TW * S) * a.csl + cvv * CH) * 2;          // this thread's first column inside a ring row
   const uint32_t col_pitch = a.csl * 2;
-  int slot = 0, tile_par = 0;
+  int slot = 0;
   uint32_t phase = 0;
   const int cs = blockIdx.x % a.n_cs, c0 = cs * a.csl + cvv * CH;
   float2 w[K * K][V], sh[V];  // BatchNorm folded: w = conv weight * scale, accumulators start from the shift
@@ -377,7 +375,7 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
     for (int kk = 0; kk < K * K; ++kk)
       w[kk][v] = __fmul2_rn(__ldg(reinterpret_cast<const float2*>(a.wkk + (size_t)kk * a.C + c0 + 2 * v)), sc);
   }
-  for (int sp = blockIdx.x / a.n_cs; sp < a.n_tiles; sp += gridDim.x / a.n_cs, tile_par ^= 1) {
+  for (int sp = blockIdx.x / a.n_cs; sp < a.n_tiles; sp += gridDim.x / a.n_cs) {
     const DwTile t = dw_decode(sp, a);
     const int ho0 = t.band * a.bh, rows = min(a.bh, a.Ho - ho0), wo0 = (t.ct * a.g + cg) * TW;
     const int hi0 = ho0 * S - PAD, r_last = (rows - 1) * S + K - 1;
@@ -452,19 +450,15 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
         }
       }
     }
-    if (a.se_sum != nullptr) {  // squeeze-excitation sums: registers -> shared (per tile) -> one global atomic per channel
-      unsigned long long* sb = sse + tile_par * a.csl;
-      if (active) {
+    // squeeze-excitation sums: one fire-and-forget 64-bit reduction per channel and thread and tile, straight to global memory
+    // (40.24 fixed point: integer adds commute, the result does not depend on arrival order).  No barrier: the tile loop of a
+    // warp never waits for the other warps of the CTA.
+    if (a.se_sum != nullptr && active) {
+      unsigned long long* sp64 = a.se_sum + (size_t)t.b * a.C + c0;
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-          atomicAdd(&sb[cvv * CH + 2 * v], static_cast<unsigned long long>(__float2ll_rn(se[v].x * SE_FIX)));
-          atomicAdd(&sb[cvv * CH + 2 * v + 1], static_cast<unsigned long long>(__float2ll_rn(se[v].y * SE_FIX)));
-        }
-      }
-      ptx::named_bar_sync(1, n_cons);
-      for (int i = tid; i < a.csl; i += n_cons) {
-        atomicAdd(a.se_sum + (size_t)t.b * a.C + cs * a.csl + i, sb[i]);
-        sb[i] = 0ull;  // this buffer is next written two tiles from now, behind the next tile's barrier
+      for (int v = 0; v < V; ++v) {
+        atomicAdd(sp64 + 2 * v, static_cast<unsigned long long>(__float2ll_rn(se[v].x * SE_FIX)));
+        atomicAdd(sp64 + 2 * v + 1, static_cast<unsigned long long>(__float2ll_rn(se[v].y * SE_FIX)));
       }
     }
   }
@@ -658,7 +652,7 @@ int launch_dwconv_tma(const __nv_bfloat16* in, int B, int H, int W, int C, int H
   const int ncw = (p.g * DW_TW - 1) * S + K;
   int rc = make_tmap_nhwc16(&map, in, B, H, W, C, p.csl, ncw);
   if (rc) return rc;
-  const size_t smem = 128 + (size_t)p.ring * p.slot_bytes + 2 * DW_MAX_RING * 8 + 2 * (size_t)p.csl * 8;
+  const size_t smem = 128 + (size_t)p.ring * p.slot_bytes + 2 * DW_MAX_RING * 8;
   static bool attr_set[64] = {};
   const int dev = current_device();
   if (!attr_set[dev]) {

@@ -33,15 +33,22 @@ struct MelTables {
   const int* mel_start;   // [128] first FFT bin of each filter
   const int* mel_off;     // [129] offsets into mel_w
   const float* mel_w;     // packed non-zero weights
+  int mel_nnz;
 };
 
+// A CTA works through CPC consecutive 8-frame chunks of one clip: the samples of chunk c+1 are fetched with cp.async into the
+// other half of a double buffer while chunk c is transformed, and the mel filter tables are read from global memory once.
+constexpr int CPC = 8;            // chunks per CTA
+constexpr int MEL_NNZ_MAX = 1280; // packed non-zero mel weights kept in shared memory (the HTK 128 x 401 bank has ~930)
+
 // smem layout (floats)
-constexpr int SM_X = 0;                           // [SPAN]
-constexpr int SM_Y = SM_X + SPAN;                 // float2 [FPC][N2][N1]  (k1 fastest)
+constexpr int SM_X = 0;                           // [2][SPAN]
+constexpr int SM_Y = SM_X + 2 * SPAN;             // float2 [FPC][N2][N1]  (k1 fastest)
 constexpr int SM_P = SM_Y + 2 * FPC * N2 * N1;    // [FPC][NBIN + 3]
 constexpr int PSTR = NBIN + 3;
-constexpr int SM_W25 = SM_P + FPC * PSTR;         // float2 [25]
-constexpr int SM_RED = SM_W25 + 2 * N1;           // [16]
+constexpr int SM_MW = SM_P + FPC * PSTR;          // [MEL_NNZ_MAX] mel weights
+constexpr int SM_MS = SM_MW + MEL_NNZ_MAX;        // int [128] first bin, int [129] offsets
+constexpr int SM_RED = SM_MS + NMEL + NMEL + 1;   // [16]
 constexpr int SMEM_FLOATS = SM_RED + 16;
 constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 
@@ -91,23 +98,46 @@ __global__ void __launch_bounds__(NTHREADS)
 melspec_kernel(const float* __restrict__ wav, long long wav_stride, int T, int frames, const MelTables tb,
                float* __restrict__ out, unsigned* __restrict__ minmax) {
   extern __shared__ float sm[];
-  float* sx = sm + SM_X;
   float2* sy = reinterpret_cast<float2*>(sm + SM_Y);
   float* sp = sm + SM_P;
-  float2* sw25 = reinterpret_cast<float2*>(sm + SM_W25);
+  float* smw = sm + SM_MW;
+  int* sms = reinterpret_cast<int*>(sm + SM_MS);
+  int* smo = sms + NMEL;
   float* sred = sm + SM_RED;
-  const int tid = threadIdx.x, b = blockIdx.y, f0 = blockIdx.x * FPC;
+  const int tid = threadIdx.x, b = blockIdx.y;
   const float* x = wav + (size_t)b * wav_stride;
+  const int chunk0 = blockIdx.x * CPC, n_chunks = (frames + FPC - 1) / FPC;
+  const int chunk_end = min(chunk0 + CPC, n_chunks);
 
-  // ---- stage 0: samples of the chunk, reflect padding (center=True) resolved on load -------------------------
-  for (int i = tid; i < SPAN; i += NTHREADS) {
-    int j = f0 * HOP + i - NFFT / 2;  // index into the unpadded clip
-    if (j < 0) j = -j;
-    if (j >= T) j = 2 * (T - 1) - j;
-    sx[i] = (j >= 0 && j < T) ? __ldg(x + j) : 0.f;
+  // samples of one chunk -> shared memory, asynchronously; reflect padding (center=True) resolved in the source index
+  auto fetch = [&](int chunk, float* dst) {
+    const int base = chunk * FPC * HOP - NFFT / 2;
+    for (int i = tid; i < SPAN; i += NTHREADS) {
+      int j = base + i;  // index into the unpadded clip
+      if (j < 0) j = -j;
+      if (j >= T) j = 2 * (T - 1) - j;
+      const bool ok = j >= 0 && j < T;
+      const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(dst + i));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(x + (ok ? j : 0)), "r"(ok ? 4 : 0) : "memory");  // (0 bytes: zero fill)
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(chunk0, sm + SM_X);
+  for (int i = tid; i < tb.mel_nnz; i += NTHREADS) smw[i] = tb.mel_w[i];
+  for (int i = tid; i < NMEL; i += NTHREADS) sms[i] = tb.mel_start[i];
+  for (int i = tid; i <= NMEL; i += NTHREADS) smo[i] = tb.mel_off[i];
+  float vmin = INFINITY, vmax = -INFINITY;
+
+  for (int chunk = chunk0; chunk < chunk_end; ++chunk) {
+  const int f0 = chunk * FPC;
+  const float* sx = sm + SM_X + ((chunk - chunk0) & 1) * SPAN;
+  if (chunk + 1 < chunk_end) {
+    fetch(chunk + 1, sm + SM_X + ((chunk + 1 - chunk0) & 1) * SPAN);  // lands while this chunk is transformed
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
-  if (tid < N1) sw25[tid] = tb.w25[tid];
-  __syncthreads();
+  __syncthreads();  // this chunk's samples (and, the first time, the tables) are visible to every thread
 
   // ---- stage 1: thread (k1 half, frame pair, n2): Y[k1] = W800^(n2 k1) * sum_n1 w[32 n1 + n2] x[f*160 + 32 n1 + n2] W25^(n1 k1) ----
   // The 25-point DFT of a REAL sequence, brute force with every W25 power an immediate operand, for TWO frames at once: the
@@ -178,20 +208,23 @@ melspec_kernel(const float* __restrict__ wav, long long wav_stride, int T, int f
   __syncthreads();
 
   // ---- mel + log + store (time-last) + per-clip min / max ---------------------------------------------------------
-  float vmin = INFINITY, vmax = -INFINITY;
   for (int i = tid; i < FPC * NMEL; i += NTHREADS) {
     const int f = i & (FPC - 1), j = i >> 3;  // consecutive threads -> consecutive frames of one mel bin
     if (f0 + f < frames) {
-      const int ks = __ldg(tb.mel_start + j), o0 = __ldg(tb.mel_off + j), o1 = __ldg(tb.mel_off + j + 1);
+      const int ks = sms[j], o0 = smo[j], o1 = smo[j + 1];
       const float* pr = sp + f * PSTR + ks;
       float acc = 0.f;
-      for (int q = 0; q < o1 - o0; ++q) acc = fmaf(pr[q], __ldg(tb.mel_w + o0 + q), acc);
+      for (int q = 0; q < o1 - o0; ++q) acc = fmaf(pr[q], smw[o0 + q], acc);
       const float y = logf(acc + 1e-6f);
       out[((size_t)b * NMEL + j) * frames + f0 + f] = y;
       vmin = fminf(vmin, y);
       vmax = fmaxf(vmax, y);
     }
   }
+  // (the next chunk's stage 1 writes sy / sp only behind its own barriers; the sample buffer it refills was last read in this
+  // chunk's stage 1, two barriers ago)
+  }  // chunk loop
+
   if (minmax != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -282,6 +315,7 @@ extern "C" int avexk_melspec_create(const float* window_host, const float* mel_f
   }
   off[NMEL] = (int)mw.size();
   if (mw.empty()) mw.push_back(0.f);
+  AVEXK_CHECK_ARG((int)mw.size() <= MEL_NNZ_MAX, "avexk_melspec_create: %d non-zero mel weights exceed the shared-memory table (%d)", (int)mw.size(), MEL_NNZ_MAX);
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
   const size_t o_win = 0, o_w25 = al(o_win + NFFT * 4), o_w800 = al(o_w25 + N1 * 8), o_ms = al(o_w800 + N2 * N1 * 8),
                o_mo = al(o_ms + NMEL * 4), o_mw = al(o_mo + (NMEL + 1) * 4), total = al(o_mw + mw.size() * 4);
@@ -311,6 +345,7 @@ extern "C" int avexk_melspec_create(const float* window_host, const float* mel_f
   h->tb.mel_start = reinterpret_cast<const int*>(d + o_ms);
   h->tb.mel_off = reinterpret_cast<const int*>(d + o_mo);
   h->tb.mel_w = reinterpret_cast<const float*>(d + o_mw);
+  h->tb.mel_nnz = (int)mw.size();
   cudaFuncSetAttribute(melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   *out = h;
   return AVEXK_OK;
@@ -338,7 +373,7 @@ extern "C" int avexk_melspec_forward(const avexk_melspec_t* h, const float* wav,
     melspec_init_minmax<<<ceil_div(B, 256), 256, 0, st>>>(mm, B);
     AVEXK_LAUNCH_CHECK();
   }
-  dim3 grid(ceil_div(frames, FPC), B);
+  dim3 grid(ceil_div(ceil_div(frames, FPC), CPC), B);
   prof_begin(st, KID_FBANK, (double)B * (4.0 * T + 4.0 * frames * NMEL));
   melspec_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(wav, wav_stride, T, frames, h->tb, out, mm);
   prof_end(st);
