@@ -319,8 +319,43 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
-        process8(v, 2 * i);
-        process8(v + 8, 2 * i + 1);
+        if (g.silu && !direct && resp == nullptr && n0 + i * 16 + 16 <= g.N) {
+          // the expand convolutions' path: all 16 columns in ONE basic block, so that the sixteen EX2 -> +1 -> RCP chains overlap
+          // (the SiLU epilogue is bound by the special-function unit; split per 8 columns it idled on each chain's latency)
+          const uint32_t ta = tab_a + (n0 + i * 16) * 4, tb = ta + g.N * 4;
+          float2 y[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 sc = lds128f(ta + k * 16), sh = lds128f(tb + k * 16);
+            y[2 * k] = __ffma2_rn(make_float2(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1])), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+            y[2 * k + 1] = __ffma2_rn(make_float2(__uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3])), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+          }
+          float2 e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 q = __fmul2_rn(y[k], make_float2(-1.4426950408889634f, -1.4426950408889634f));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k].x) : "f"(q.x));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[k].y) : "f"(q.y));
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 d = __fadd2_rn(e[k], make_float2(1.0f, 1.0f));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[k].x) : "f"(d.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[k].y) : "f"(d.y));
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float2 r = __fmul2_rn(y[k], e[k]);
+            pk[k] = pack_h16(r.x, r.y);
+          }
+          const uint32_t rowa = stg + box_par * PW_BOX_BYTES + lane * 128;
+          sts128u(rowa + ((((2 * i) & 7) ^ sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128u(rowa + ((((2 * i + 1) & 7) ^ sw) << 4), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+        } else {
+          process8(v, 2 * i);
+          process8(v + 8, 2 * i + 1);
+        }
         if (!direct && ((i & 3) == 3 || i == nch - 1)) {
           ptx::fence_proxy_async();  // the warp's shared-memory writes -> visible to the TMA store
           __syncwarp();
