@@ -5,10 +5,11 @@ OUT = os.path.join(ROOT, "profiles")
 
 KNOWN = ("gemm_bf16_kernel", "attention_tc_kernel", "attention_gated_kernel", "posconv_kernel", "layernorm_kernel", "fbank_kernel",
          "patchify_kernel", "group_pad_kernel", "mean_pool_kernel", "f32_to_bf16", "posconv_pack", "posconv_norm", "gate_pack",
-         "melspec", "dwconv_kernel", "se_mlp_kernel", "se_apply_kernel", "stem_kernel")
+         "melspec_kernel", "melspec_normalise", "melspec_init", "dwconv_tma_kernel", "dwconv_kernel", "pointwise_kernel", "se_mlp_kernel",
+         "se_apply_kernel", "stem_kernel", "nhwc_to_nchw_kernel")
 
 
-def launches(csv_path, out_name):
+def launches(csv_path, out_name, span_marker=None):
     """Per-kernel launch list: count, device time and share; DRAM bytes per launch when the capture holds them
     (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum)."""
     rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
@@ -25,6 +26,8 @@ def launches(csv_path, out_name):
             if k in name:
                 name = k
         # template arguments distinguish the GEMM epilogues: keep mode / pair / warps
+        if name == "dwconv_tma_kernel" and "<" in r[kn]:
+            name += "<" + r[kn].split("<", 1)[-1].split(">")[0].replace("(int)", "").replace(", ", " ") + ">"  # <K S CH>
         if name == "gemm_bf16_kernel" and "<" in r[kn]:
             name += "<" + r[kn].split("<", 2)[-1].split(">")[0].replace("(int)", "").replace("(bool)", "") + ">"
         e = per.setdefault(r[idc], {"name": name, "ms": 0.0, "rd": None, "wr": None})
@@ -34,6 +37,11 @@ def launches(csv_path, out_name):
             e["rd"] = v * scale.get(unit, 1.0)
         elif r[mn].startswith("dram__bytes_write"):
             e["wr"] = v * scale.get(unit, 1.0)
+    if span_marker:  # keep ONE complete pass: from the first launch of `span_marker` to the one before its next occurrence
+        ids = list(per)
+        marks = [i for i, k in enumerate(ids) if per[k]["name"].startswith(span_marker)]
+        if len(marks) >= 2:
+            per = collections.OrderedDict((k, per[k]) for k in ids[marks[0]:marks[1]])
     agg = collections.OrderedDict()
     total = 0.0
     for e in per.values():
@@ -54,7 +62,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu.sum", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__maximum_warps_per_active_cycle_pct"]
 
 def full(rep, out_name):
@@ -79,5 +88,7 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     if os.path.exists(os.path.join(g, f"launches_{tag}.csv")):
         launches(os.path.join(g, f"launches_{tag}.csv"), f"launches_{tag}.csv")
+    if os.path.exists(os.path.join(g, f"launches_effnet_{tag}.csv")):  # one complete EfficientNet forward
+        launches(os.path.join(g, f"launches_effnet_{tag}.csv"), f"launches_effnet_{tag}.csv", span_marker="melspec_init")
     for rep in sys.argv[2:]:
         full(os.path.join(g, rep + ".ncu-rep"), rep + "_summary.json")
