@@ -347,7 +347,10 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
         for (int r = 0; r < nsteps; ++r) {
           const int hi = hi0 + r;
           if ((unsigned)hi >= (unsigned)a.H) continue;  // a padding row: the consumers know, nothing is sent
-          while (!ptx::mbar_try_wait_a(empty_a + slot * 8, phase ^ 1)) __nanosleep(64);  // (back-off: the ring is rows deep)
+          for (uint32_t spins = 0; !ptx::mbar_try_wait_a(empty_a + slot * 8, phase ^ 1);) {  // back-off: the ring is rows deep
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();  // a protocol bug fails the launch instead of hanging the GPU
+          }
           ptx::mbar_arrive_expect_tx_a(full_a + slot * 8, a.row_bytes);
           ptx::tma_load_4d_a(ring_a + slot * a.slot_bytes, &map_in, full_a + slot * 8, cs * a.csl, wi0, hi, t.b);
           if (++slot == a.ring) { slot = 0; phase ^= 1; }
@@ -467,28 +470,55 @@ dwconv_tma_kernel(const __grid_constant__ CUtensorMap map_in, const DwTmaArgs a)
 // ---------------------------------------------------------------------------------------------------------
 // squeeze-excitation MLP per clip: s = sigmoid(W2 silu(W1 avg + b1) + b2)
 // ---------------------------------------------------------------------------------------------------------
+constexpr int SE_CL = 4;  // clips per CTA: a weight row read from L2 serves four clips (one clip per CTA re-read 442 KB of
+                          // weights per clip at C = 1152); the loops keep several independent loads in flight per thread
 __global__ void __launch_bounds__(256)
-se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int C, int S, const float* __restrict__ w1,
+se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int B, int C, int S, const float* __restrict__ w1,
               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
               float* __restrict__ se_scale) {
-  extern __shared__ float sm[];  // avg[C], hid[S]
+  extern __shared__ float sm[];  // avg[SE_CL][C], hid[SE_CL][S]
   float* avg = sm;
-  float* hid = sm + C;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int c = tid; c < C; c += blockDim.x)
-    avg[c] = static_cast<float>(static_cast<double>(static_cast<long long>(se_sum[(size_t)b * C + c])) * (1.0 / SE_FIX)) * inv_hw;
+  float* hid = sm + SE_CL * C;
+  const int b0 = blockIdx.x * SE_CL, nb = min(SE_CL, B - b0), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < SE_CL * C; i += blockDim.x) {
+    const int q = i / C, c = i - q * C;
+    avg[i] = q < nb ? static_cast<float>(static_cast<double>(static_cast<long long>(se_sum[(size_t)(b0 + q) * C + c])) * (1.0 / SE_FIX)) * inv_hw
+                    : 0.f;
+  }
   __syncthreads();
   for (int j = warp; j < S; j += blockDim.x / 32) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + (size_t)j * C + c), avg[c], a);
-    a = warp_sum(a);
-    if (lane == 0) hid[j] = silu(a + __ldg(b1 + j));
+    float a[SE_CL];
+#pragma unroll
+    for (int q = 0; q < SE_CL; ++q) a[q] = 0.f;
+    const float* wr = w1 + (size_t)j * C;
+#pragma unroll 4
+    for (int c = lane; c < C; c += 32) {
+      const float w = __ldg(wr + c);
+#pragma unroll
+      for (int q = 0; q < SE_CL; ++q) a[q] = fmaf(w, avg[q * C + c], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < SE_CL; ++q) {
+      const float v = warp_sum(a[q]);
+      if (lane == 0) hid[q * S + j] = silu(v + __ldg(b1 + j));
+    }
   }
   __syncthreads();
   for (int c = tid; c < C; c += blockDim.x) {
-    float a = __ldg(b2 + c);
-    for (int j = 0; j < S; ++j) a = fmaf(__ldg(w2 + (size_t)c * S + j), hid[j], a);
-    se_scale[(size_t)b * C + c] = 1.0f / (1.0f + __expf(-a));
+    float a[SE_CL];
+    const float bias = __ldg(b2 + c);
+#pragma unroll
+    for (int q = 0; q < SE_CL; ++q) a[q] = bias;
+    const float* wr = w2 + (size_t)c * S;
+#pragma unroll 8
+    for (int j = 0; j < S; ++j) {
+      const float w = __ldg(wr + j);
+#pragma unroll
+      for (int q = 0; q < SE_CL; ++q) a[q] = fmaf(w, hid[q * S + j], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < SE_CL; ++q)
+      if (q < nb) se_scale[(size_t)(b0 + q) * C + c] = 1.0f / (1.0f + __expf(-a[q]));
   }
 }
 
@@ -967,8 +997,10 @@ extern "C" int avexk_effnet_forward(avexk_effnet_t* h, const float* mel, const v
     AVEXK_CUDA(cudaMemsetAsync(se_sum, 0, sizeof(unsigned long long) * (size_t)B * c.cexp, st));
     TRY(launch_dwconv(dw_in, B, H, W, c.cexp, c.kernel, c.stride, b.dw_w, b.dw_scale, b.dw_shift, dw, se_sum, st));
     TRY(dbg("depthwise", i));
-    se_mlp_kernel<<<B, 256, (c.cexp + c.csq) * sizeof(float), st>>>(se_sum, 1.0f / (float)(Ho * Wo), c.cexp, c.csq, b.se1_w, b.se1_b,
-                                                                    b.se2_w, b.se2_b, se_scale);
+    if (SE_CL * (c.cexp + c.csq) * sizeof(float) > 48 * 1024)  // (only wider variants than B0 get here)
+      AVEXK_CUDA(cudaFuncSetAttribute(se_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    se_mlp_kernel<<<ceil_div(B, SE_CL), 256, SE_CL * (c.cexp + c.csq) * sizeof(float), st>>>(se_sum, 1.0f / (float)(Ho * Wo), B, c.cexp, c.csq,
+                                                                                             b.se1_w, b.se1_b, b.se2_w, b.se2_b, se_scale);
     AVEXK_LAUNCH_CHECK();
     const long long Mo = (long long)B * Ho * Wo;
     const bool use_res = c.stride == 1 && c.cin == c.cout;

@@ -149,7 +149,7 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int mt = tile / g.n_nt, nt = tile - mt * g.n_nt;
+        const int mt = g.n_nt == 1 ? tile : tile / g.n_nt, nt = tile - mt * g.n_nt;  // (no division on the common single-N-tile path)
         for (int kb = 0; kb < g.kblocks; ++kb) {
           pw_wait_relaxed(&a_empty[stage], phase ^ 1);
           unsigned char* dst = smem + stage * g.stage_bytes;
@@ -208,7 +208,7 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       jcol[i] = (j ^ (row & 7)) << 3;          // logical k (inside the k-block) of that chunk under the 128-byte swizzle
     }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int mt = tile / g.n_nt;
+      const int mt = g.n_nt == 1 ? tile : tile / g.n_nt;
       if (mt != last_mt) {  // this thread's row moved: one N tile per row block -> by exactly one grid stride, no division
         if (g.n_nt == 1) {
           clip += dq; rem += dr;
@@ -277,13 +277,17 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool direct = g.direct != 0;
     const uint32_t stg = smem_a + g.off_ob + (warp - PW_WARP_SCALE0) * (2 * PW_BOX_BYTES);  // this warp's two staging boxes
     const uint32_t sw = lane & 7;
-    int it = 0;
     uint32_t box_par = 0;  // staging box in use (alternates per 64-column box)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      if (it % ne != sub) continue;  // (a warp with sub >= ne has no tiles)
-      const int acc = it % g.acc_stages;
-      const uint32_t acc_phase = (it / g.acc_stages) & 1;
-      const int mt = tile / g.n_nt, nt = tile - mt * g.n_nt;
+    // counters instead of divisions by run-time values: `turn` = tile ordinal modulo ne, (acc, acc_phase) = the accumulator ring
+    int turn = 0, acc = -1;
+    uint32_t acc_phase = 1;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (++acc == g.acc_stages) acc = 0;
+      if (acc == 0) acc_phase ^= 1;
+      const bool mine = turn == sub;  // (a warp with sub >= ne has no tiles)
+      if (++turn == ne) turn = 0;
+      if (!mine) continue;
+      const int mt = g.n_nt == 1 ? tile : tile / g.n_nt, nt = tile - mt * g.n_nt;
       const int grow = mt * PW_BM + row, n0 = nt * g.ntb;
       const __nv_bfloat16* resp = g.res != nullptr && grow < g.M ? g.res + (size_t)grow * g.N + n0 : nullptr;
       __nv_bfloat16* outp = g.out + (size_t)grow * g.N + n0;

@@ -1,6 +1,8 @@
 # Final round-2 evidence: the commands whose outputs are summarised under profiles/ (tools/summarize_profiles.py r2_final ...).
 set -x
 mkdir -p gpurun_out
+# 0. parity suite on this build
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/gputest_r2_final2.log
 # 1. the bench line itself (CUDA-event timing, no profiler attached) and the EfficientNet line
 timeout 700 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2_final2.log 2>&1
 timeout 300 python bench.py --workload effnet --steps 10 --warmup 3 > gpurun_out/bench_effnet_r2_final.log 2>&1
@@ -17,7 +19,6 @@ timeout 600 ncu --set full --clock-control none -k regex:pointwise_kernel -s 93 
 timeout 400 ncu --set full --clock-control none -k regex:"melspec_kernel|stem_kernel" -s 6 -c 2 -o gpurun_out/mel_r2_final \
   python bench.py --workload effnet --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_mel_r2_final.log 2>&1
 # 4. parity suite on this build, stress test, compute-sanitizer on the new EfficientNet kernels
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/gputest_r2_final2.log
 timeout 300 python tools/stress_pointwise.py 20 > gpurun_out/stress_r2_final.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_effnet_gpu.py -q -k "conv1x1 or dwconv or melspec" 2>&1 | tail -25 > gpurun_out/memcheck_effnet_r2_final.log
 timeout 900 compute-sanitizer --tool synccheck python -m pytest tests/test_effnet_gpu.py -q -k "conv1x1 or dwconv" 2>&1 | tail -25 > gpurun_out/synccheck_effnet_r2_final.log
