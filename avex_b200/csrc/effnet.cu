@@ -491,8 +491,8 @@ se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int B
 #pragma unroll
     for (int q = 0; q < SE_CL; ++q) a[q] = 0.f;
     const float* wr = w1 + (size_t)j * C;
-#pragma unroll 4
-    for (int c = lane; c < C; c += 32) {
+#pragma unroll 12
+    for (int c = lane; c < C; c += 32) {  // (twelve weight loads in flight per lane: the row is read once, from L2)
       const float w = __ldg(wr + c);
 #pragma unroll
       for (int q = 0; q < SE_CL; ++q) a[q] = fmaf(w, avg[q * C + c], a[q]);
@@ -510,11 +510,25 @@ se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int B
 #pragma unroll
     for (int q = 0; q < SE_CL; ++q) a[q] = bias;
     const float* wr = w2 + (size_t)c * S;
-#pragma unroll 8
-    for (int j = 0; j < S; ++j) {
-      const float w = __ldg(wr + j);
+    if ((S & 3) == 0) {  // 16-byte weight loads (S = 8, 4 .. 48 in B0: every squeeze width is a multiple of 4)
+#pragma unroll 6
+      for (int j = 0; j < S; j += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wr + j));
 #pragma unroll
-      for (int q = 0; q < SE_CL; ++q) a[q] = fmaf(w, hid[q * S + j], a[q]);
+        for (int q = 0; q < SE_CL; ++q) {
+          a[q] = fmaf(w.x, hid[q * S + j], a[q]);
+          a[q] = fmaf(w.y, hid[q * S + j + 1], a[q]);
+          a[q] = fmaf(w.z, hid[q * S + j + 2], a[q]);
+          a[q] = fmaf(w.w, hid[q * S + j + 3], a[q]);
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int j = 0; j < S; ++j) {
+        const float w = __ldg(wr + j);
+#pragma unroll
+        for (int q = 0; q < SE_CL; ++q) a[q] = fmaf(w, hid[q * S + j], a[q]);
+      }
     }
 #pragma unroll
     for (int q = 0; q < SE_CL; ++q)
