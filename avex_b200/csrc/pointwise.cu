@@ -188,8 +188,79 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == g.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (se && warp < PW_WARP_SE_EPI0) {
+  } else if (se && warp < PW_WARP_SE_EPI0 && g.hw >= PW_BM && g.n_nt == 1) {
     // ===================== squeeze-excitation scalers: A[row, :] *= se[clip(row), :] in shared memory =====================
+    // (clips of at least 128 rows: the high-resolution layers, where this path matters)
+    // A thread owns ONE logical 8-column chunk j of the k-block for four rows 32 apart: it needs 8 scale values per clip and
+    // stage (32 bytes) instead of 32 per row, so the values of the NEXT stage -- next k-block, or the first k-block of the
+    // CTA's next tile -- fit in registers and are fetched one stage ahead: their L2 latency (the scale table was just written
+    // by the SE kernel) hides behind the current stage instead of stalling it (36 % of the scaler's time in ncu).  A tile of
+    // 128 rows meets at most one clip boundary (hw >= 128): rows past it use the second value set.  The 8 lanes of a
+    // quarter-warp read the 8 chunks of one row: conflict-free.
+    const int t = threadIdx.x - PW_WARP_SCALE0 * 32, j = t & 7, rbase = t >> 3;  // rows rbase + 32 i
+    uint32_t roff[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = rbase + 32 * i;
+      roff[i] = row * 128 + ((j ^ (row & 7)) << 4);  // physical position of logical chunk j under the 128-byte swizzle
+    }
+    const int n_clips = (g.M + g.hw - 1) / g.hw;
+    const int step_rows = gridDim.x * PW_BM, dq = step_rows / g.hw, dr = step_rows - dq * g.hw;
+    int grow0 = blockIdx.x * PW_BM + rbase, clip = grow0 / g.hw, rem = grow0 - clip * g.hw;
+    auto load_scales = [&](int clipA, int remA, int kb, float4 (&a)[2], float4 (&b)[2]) {
+      const int col = kb * PW_BK + j * 8;
+      if (col >= g.K || clipA >= n_clips) return;
+      const float* sp = g.se_scale + (size_t)clipA * g.K + col;
+      a[0] = __ldg(reinterpret_cast<const float4*>(sp));
+      a[1] = __ldg(reinterpret_cast<const float4*>(sp + 4));
+      if (remA + 96 >= g.hw && clipA + 1 < n_clips) {  // one of this thread's rows lies in the next clip
+        b[0] = __ldg(reinterpret_cast<const float4*>(sp + g.K));
+        b[1] = __ldg(reinterpret_cast<const float4*>(sp + g.K + 4));
+      }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    float4 ca[2], cb[2];
+    if ((int)blockIdx.x < n_tiles) load_scales(clip, rem, 0, ca, cb);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int ntile = tile + gridDim.x;
+      int nclip = clip + dq, nrem = rem + dr;  // row state of the CTA's next tile (one grid stride further)
+      if (nrem >= g.hw) { nrem -= g.hw; ++nclip; }
+      for (int kb = 0; kb < g.kblocks; ++kb) {
+        float4 na[2], nb[2];
+        if (kb + 1 < g.kblocks) load_scales(clip, rem, kb + 1, na, nb);
+        else if (ntile < n_tiles) load_scales(nclip, nrem, 0, na, nb);
+        ptx::mbar_wait(&a_full[stage], phase);
+        if (kb * PW_BK + j * 8 < g.K) {
+          const uint32_t base = smem_a + stage * g.stage_bytes;
+          uint4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (grow0 + 32 * i < g.M) v[i] = lds128u(base + roff[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (grow0 + 32 * i >= g.M) continue;
+            const bool second = rem + 32 * i >= g.hw;  // this row belongs to the next clip
+            const float4 s0 = second ? cb[0] : ca[0], s1 = second ? cb[1] : ca[1];
+            const float2 a = unpack_h16(v[i].x), b = unpack_h16(v[i].y), c = unpack_h16(v[i].z), d = unpack_h16(v[i].w);
+            uint4 o;
+            o.x = pack_h16(a.x * s0.x, a.y * s0.y);
+            o.y = pack_h16(b.x * s0.z, b.y * s0.w);
+            o.z = pack_h16(c.x * s1.x, c.y * s1.y);
+            o.w = pack_h16(d.x * s1.z, d.y * s1.w);
+            sts128u(base + roff[i], o);
+          }
+        }
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
+        if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        ca[0] = na[0]; ca[1] = na[1]; cb[0] = nb[0]; cb[1] = nb[1];
+      }
+      grow0 += step_rows; clip = nclip; rem = nrem;
+    }
+  } else if (se && warp < PW_WARP_SE_EPI0) {
+    // ===================== squeeze-excitation scalers, general form (clips shorter than a tile, or several N tiles) ==========
     // Eight warps, two threads per A row (four 16-byte chunks each).  The clip's scale values are fetched BEFORE the wait on
     // the stage (they depend only on the tile), and a thread's chunks are read together, so a stage costs one shared-memory
     // round trip, not a chain of dependent global loads.  The clip index advances incrementally (no division per tile).
@@ -308,7 +379,8 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           y0 = pw_silu2(y0); y1 = pw_silu2(y1); y2 = pw_silu2(y2); y3 = pw_silu2(y3);
         }
         if (resp != nullptr) {
-          const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + c8 * 8));
+          uint4 rv;  // streamed once: keep it out of the (small, ~28 KB beside 228 KB of shared memory) L1 that holds the SE scale rows
+          asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "l"(resp + c8 * 8));
           y0 = __fadd2_rn(y0, unpack_h16(rv.x)); y1 = __fadd2_rn(y1, unpack_h16(rv.y));
           y2 = __fadd2_rn(y2, unpack_h16(rv.z)); y3 = __fadd2_rn(y3, unpack_h16(rv.w));
         }
