@@ -480,27 +480,50 @@ se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int B
   float* avg = sm;
   float* hid = sm + SE_CL * C;
   const int b0 = blockIdx.x * SE_CL, nb = min(SE_CL, B - b0), tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#pragma unroll 4
   for (int i = tid; i < SE_CL * C; i += blockDim.x) {
     const int q = i / C, c = i - q * C;
     avg[i] = q < nb ? static_cast<float>(static_cast<double>(static_cast<long long>(se_sum[(size_t)(b0 + q) * C + c])) * (1.0 / SE_FIX)) * inv_hw
                     : 0.f;
   }
   __syncthreads();
-  for (int j = warp; j < S; j += blockDim.x / 32) {
-    float a[SE_CL];
+  // hidden layer: warp w owns rows w, w + 8, ...; a lane reads four consecutive weights per 16-byte load and keeps the loads of
+  // three rows in flight (the 221 KB of W1 at C = 1152 stream through the SM once; with one 4-byte load per lane and step this
+  // phase alone took 17 us)
+  for (int j0 = warp; j0 < S; j0 += 3 * (blockDim.x / 32)) {
+    float a[3][SE_CL];
 #pragma unroll
-    for (int q = 0; q < SE_CL; ++q) a[q] = 0.f;
-    const float* wr = w1 + (size_t)j * C;
-#pragma unroll 12
-    for (int c = lane; c < C; c += 32) {  // (twelve weight loads in flight per lane: the row is read once, from L2)
-      const float w = __ldg(wr + c);
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int q = 0; q < SE_CL; ++q) a[q] = fmaf(w, avg[q * C + c], a[q]);
+      for (int q = 0; q < SE_CL; ++q) a[r][q] = 0.f;
+#pragma unroll 2
+    for (int c = 4 * lane; c < C; c += 128) {
+      float4 w[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int j = j0 + r * (blockDim.x / 32);
+        w[r] = j < S ? __ldg(reinterpret_cast<const float4*>(w1 + (size_t)j * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < SE_CL; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(avg + q * C + c);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          a[r][q] = fmaf(w[r].x, v.x, a[r][q]);
+          a[r][q] = fmaf(w[r].y, v.y, a[r][q]);
+          a[r][q] = fmaf(w[r].z, v.z, a[r][q]);
+          a[r][q] = fmaf(w[r].w, v.w, a[r][q]);
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < SE_CL; ++q) {
-      const float v = warp_sum(a[q]);
-      if (lane == 0) hid[q * S + j] = silu(v + __ldg(b1 + j));
+    for (int r = 0; r < 3; ++r) {
+      const int j = j0 + r * (blockDim.x / 32);
+#pragma unroll
+      for (int q = 0; q < SE_CL; ++q) {
+        const float v = warp_sum(a[r][q]);
+        if (lane == 0 && j < S) hid[q * S + j] = silu(v + __ldg(b1 + j));
+      }
     }
   }
   __syncthreads();
@@ -511,7 +534,7 @@ se_mlp_kernel(const unsigned long long* __restrict__ se_sum, float inv_hw, int B
     for (int q = 0; q < SE_CL; ++q) a[q] = bias;
     const float* wr = w2 + (size_t)c * S;
     if ((S & 3) == 0) {  // 16-byte weight loads (S = 8, 4 .. 48 in B0: every squeeze width is a multiple of 4)
-#pragma unroll 6
+#pragma unroll 12
       for (int j = 0; j < S; j += 4) {
         const float4 w = __ldg(reinterpret_cast<const float4*>(wr + j));
 #pragma unroll
