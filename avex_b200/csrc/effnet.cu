@@ -10,15 +10,15 @@
 // in eval mode, SiLU, squeeze-excitation), `avgpool` and the classifier.
 //   * the 3 identical input channels are never materialised: the stem kernel uses the conv weights summed over C_in and
 //     applies the per-clip min-max normalisation of the mel image (audio_utils.py:167-172) on load;
-//   * activations live in HBM as NHWC fp16, so every 1x1 convolution (88 % of the MACs) is a plain GEMM
-//     [B*H*W, C_in] x [C_out, C_in]^T on the tcgen05 kernel of gemm_tc.cu with the folded BatchNorm, SiLU and the
-//     residual add in its epilogue; the raw (pre-BN) conv output that a forward hook on `block.3.0` / `features.8.0`
-//     sees is stored from the same epilogue when requested;
-//   * depthwise k x k convolutions are memory-bound stencils: one thread = 8 channels (one 16-byte vector) of one output
-//     pixel, BN + SiLU fused, and the squeeze-excitation global average accumulated on the way out (registers ->
-//     shared-memory atomics -> one global atomic per (CTA, channel));
-//   * SE: a tiny per-clip MLP kernel, then the channel scale applied in place.
-// Roofline: HBM (about 29 FLOP/B overall); the pointwise GEMMs are reported against the tensor pipe.
+//   * activations live in HBM as NHWC fp16, so every 1x1 convolution (88 % of the MACs) is a GEMM [B*H*W, C_in] x [C_out, C_in]^T:
+//     the memory-bound tcgen05 kernel of pointwise.cu (folded BatchNorm, SiLU, residual add in its epilogue, the squeeze-
+//     excitation rescale of the project convolution's input on its A operand); when a forward hook asks for the raw (pre-BN)
+//     conv output of `block.3.0` / `features.8.0`, the general GEMM of gemm_tc.cu stores it from its epilogue instead;
+//   * depthwise k x k convolutions: a TMA-fed sliding-window kernel (dwconv_tma_kernel below: input rows through a shared-
+//     memory ring, weights and a rotating window of output-row accumulators in registers), BN + SiLU fused, the squeeze-
+//     excitation sums leaving as 64-bit fixed-point reductions; the round-1 per-output-row kernel stays as the fallback;
+//   * SE: a small MLP kernel (four clips per CTA) produces the channel scales that the project convolution applies.
+// Roofline: HBM (about 29 FLOP/B overall); per kernel family the binding unit differs.
 #include <stdlib.h>
 
 #include <vector>
