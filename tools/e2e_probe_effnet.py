@@ -7,15 +7,13 @@ import torch
 
 from avex_b200 import plugin
 from avex_b200.plugin import efficientnet_model  # noqa: F401
-from oracle.weights import make_effnet_weights
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 spec = plugin.ModelSpec(name="efficientnet", device="cuda", efficientnet_variant="b0",
                         audio_config=dict(sample_rate=16000, n_fft=800, hop_length=160, win_length=800, window="hann", n_mels=128,
                                           representation="mel_spectrogram", normalize=True, target_length_seconds=10, window_selection="random"))
 model = plugin.build_model_from_spec(spec, "cuda", pretrained=False, return_features_only=True).eval()
-W = make_effnet_weights(seed=3, num_classes=0, bn_stats=dict(np.load(os.path.join(ROOT, "tests", "golden", "effnet_bn_stats.npz"))))
-model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in W.items()}, strict=False)
+# (timing only: the module's own random initialisation; bench.py loads seeded weights with calibrated BatchNorm statistics)
 B, T = 512, 80000
 wav = torch.randn(B, T, device="cuda") * 0.1
 host = [torch.empty(B, T).pin_memory() for _ in range(2)]
