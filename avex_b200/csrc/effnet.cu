@@ -12,8 +12,9 @@
 //     applies the per-clip min-max normalisation of the mel image (audio_utils.py:167-172) on load;
 //   * activations live in HBM as NHWC fp16, so every 1x1 convolution (88 % of the MACs) is a GEMM [B*H*W, C_in] x [C_out, C_in]^T:
 //     the memory-bound tcgen05 kernel of pointwise.cu (folded BatchNorm, SiLU, residual add in its epilogue, the squeeze-
-//     excitation rescale of the project convolution's input on its A operand); when a forward hook asks for the raw (pre-BN)
-//     conv output of `block.3.0` / `features.8.0`, the general GEMM of gemm_tc.cu stores it from its epilogue instead;
+//     excitation rescale of the project convolution's input on its A operand, and -- when a forward hook on `block.3.0` /
+//     `block.2.0` asks for it -- an fp32 copy of the raw pre-BN accumulators); the head convolution (fp32 NCHW features)
+//     runs on the general GEMM of gemm_tc.cu;
 //   * depthwise k x k convolutions: a TMA-fed sliding-window kernel (dwconv_tma_kernel below: input rows through a shared-
 //     memory ring, weights and a rotating window of output-row accumulators in registers), BN + SiLU fused, the squeeze-
 //     excitation sums leaving as 64-bit fixed-point reductions; the round-1 per-output-row kernel stays as the fallback;
@@ -778,14 +779,14 @@ int launch_dwconv(const __nv_bfloat16* in, int B, int H, int W, int C, int k, in
   return AVEXK_OK;
 }
 
-// 1x1 convolution dispatch: the memory-bound kernel (pointwise.cu) whenever the request fits it (fp16 output, no raw copy);
-// the general GEMM otherwise.  AVEXK_PW=0 (measurement switch) forces the general GEMM.  A squeeze-excitation scale on the A
+// 1x1 convolution dispatch: the memory-bound kernel (pointwise.cu) whenever the request has an fp16 output (the raw pre-BN copy
+// a forward hook asks for rides along); the general GEMM otherwise (fp32 output: the head convolution).  AVEXK_PW=0 (measurement switch) forces the general GEMM.  A squeeze-excitation scale on the A
 // operand is fused by the pointwise kernel; on the general path it is applied in place first.
 int conv1x1_any(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
                 const __nv_bfloat16* res, const float* se_scale, int hw, float* raw_out, void* out, int out_16bit, cudaStream_t st) {
   static const int use_pw = [] { const char* e = getenv("AVEXK_PW"); return e ? atoi(e) : 1; }();
-  if (use_pw && pointwise_supported(N, K, raw_out, out, out_16bit))
-    return pointwise_launch(A, W, M, N, K, scale, shift, silu, res, se_scale, hw, out, st);
+  if (use_pw && pointwise_supported(N, K, out, out_16bit))
+    return pointwise_launch(A, W, M, N, K, scale, shift, silu, res, se_scale, hw, raw_out, out, st);
   if (se_scale != nullptr && M > 0) {
     const long long per_clip_vec = (long long)hw * (K / 8), total = (long long)M * (K / 8);
     int grid = ceil_div(total, 256);
@@ -813,8 +814,8 @@ extern "C" int avexk_conv1x1_se_f16(const void* A, const float* se_scale, int ro
                                      const float* scale, const float* shift, const void* res_f16, void* out, void* stream) {
   using namespace avexk;
   AVEXK_CHECK_ARG(A && W && out && se_scale && M >= 0 && rows_per_clip > 0, "avexk_conv1x1_se_f16: bad argument");
-  AVEXK_CHECK_ARG(pointwise_supported(N, K, nullptr, out, 1), "avexk_conv1x1_se_f16: K and N must be multiples of 8 (K=%d N=%d)", K, N);
-  return pointwise_launch(A, W, M, N, K, scale, shift, 0, reinterpret_cast<const __nv_bfloat16*>(res_f16), se_scale, rows_per_clip, out,
+  AVEXK_CHECK_ARG(pointwise_supported(N, K, out, 1), "avexk_conv1x1_se_f16: K and N must be multiples of 8 (K=%d N=%d)", K, N);
+  return pointwise_launch(A, W, M, N, K, scale, shift, 0, reinterpret_cast<const __nv_bfloat16*>(res_f16), se_scale, rows_per_clip, nullptr, out,
                           reinterpret_cast<cudaStream_t>(stream));
 }
 

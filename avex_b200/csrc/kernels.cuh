@@ -21,9 +21,9 @@ int gemm_bf16_ln_launch(const void* A, long long lda, const void* W, long long l
                         float* ln_out_f32, __nv_bfloat16* ln_out_bf16, void* scratch, size_t scratch_bytes, int zero_counters,
                         cudaStream_t st, long long* pool_raw = nullptr, long long* pool_y = nullptr, int pool_rows = 0);
 // pointwise.cu: the memory-bound form of the 1x1 convolution (fp16 out, optional squeeze-excitation scale on the A operand)
-bool pointwise_supported(int N, int K, const float* raw_out, const void* out, int out_16bit);
+bool pointwise_supported(int N, int K, const void* out, int out_16bit);
 int pointwise_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
-                     const __nv_bfloat16* res, const float* se_scale, int hw, void* out, cudaStream_t st);
+                     const __nv_bfloat16* res, const float* se_scale, int hw, float* raw_out, void* out, cudaStream_t st);
 int conv1x1_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
                    const __nv_bfloat16* res, float* raw_out, void* out, int out_bf16, cudaStream_t st);
 // attention_tc.cu

@@ -44,6 +44,7 @@ struct PwArgs {
   const float *scale, *shift, *se_scale;
   const __nv_bfloat16* res;
   __nv_bfloat16* out;
+  float* raw;  // optional fp32 copy of the accumulators (the pre-BatchNorm tensor a forward hook on the conv sees)
 };
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -369,6 +370,11 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       auto process8 = [&](const uint32_t* v, int c8) {  // 8 columns starting at tile column c8 * 8
         const int col = n0 + c8 * 8;
         if (col >= g.N) return;  // (warp-uniform) zero-padded columns of the last N tile
+        if (g.raw != nullptr && grow < g.M) {
+          float4* rp = reinterpret_cast<float4*>(g.raw + (size_t)grow * g.N + col);
+          rp[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          rp[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        }
         const float4 sc0 = lds128f(tab_a + col * 4), sc1 = lds128f(tab_a + col * 4 + 16);
         const float4 sh0 = lds128f(tab_a + (g.N + col) * 4), sh1 = lds128f(tab_a + (g.N + col) * 4 + 16);
         float2 y0 = __ffma2_rn(make_float2(__uint_as_float(v[0]), __uint_as_float(v[1])), make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
@@ -395,7 +401,7 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
-        if (g.silu && !direct && resp == nullptr && n0 + i * 16 + 16 <= g.N) {
+        if (g.silu && !direct && resp == nullptr && g.raw == nullptr && n0 + i * 16 + 16 <= g.N) {
           // the expand convolutions' path: all 16 columns in ONE basic block, so that the sixteen activation chains overlap
           const uint32_t ta = tab_a + (n0 + i * 16) * 4, tb = ta + g.N * 4;
           float2 y[8];
@@ -483,14 +489,14 @@ pointwise_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 }  // namespace
 
-// Whether the memory-bound kernel takes this 1x1 convolution (else the general GEMM does): fp16 output, no raw (pre-BN) copy.
-bool pointwise_supported(int N, int K, const float* raw_out, const void* out, int out_16bit) {
-  return raw_out == nullptr && out != nullptr && out_16bit && N % 8 == 0 && K % 8 == 0 && N >= 8 && K >= 8;
+// Whether the memory-bound kernel takes this 1x1 convolution (else the general GEMM does): it always writes an fp16 output.
+bool pointwise_supported(int N, int K, const void* out, int out_16bit) {
+  return out != nullptr && out_16bit && N % 8 == 0 && K % 8 == 0 && N >= 8 && K >= 8;
 }
 
 int pointwise_launch(const void* A, const void* W, int M, int N, int K, const float* scale, const float* shift, int silu,
-                     const __nv_bfloat16* res, const float* se_scale, int hw, void* out, cudaStream_t st) {
-  AVEXK_CHECK_ARG(pointwise_supported(N, K, nullptr, out, 1), "pointwise: unsupported shape N=%d K=%d", N, K);
+                     const __nv_bfloat16* res, const float* se_scale, int hw, float* raw_out, void* out, cudaStream_t st) {
+  AVEXK_CHECK_ARG(pointwise_supported(N, K, out, 1), "pointwise: unsupported shape N=%d K=%d", N, K);
   AVEXK_CHECK_ARG(se_scale == nullptr || hw > 0, "pointwise: squeeze-excitation scale needs rows per clip");
   if (M == 0) return AVEXK_OK;
   PwArgs g{};
@@ -525,6 +531,7 @@ int pointwise_launch(const void* A, const void* W, int M, int N, int K, const fl
   g.silu = silu; g.hw = hw;
   g.scale = scale; g.shift = shift; g.se_scale = se_scale; g.res = res;
   g.out = reinterpret_cast<__nv_bfloat16*>(out);
+  g.raw = raw_out;
   CUtensorMap map_a, map_w, map_out;
   int rc = make_tmap_2d_bf16(&map_a, A, M, K, K, PW_BM, PW_BK);
   if (rc) return rc;
