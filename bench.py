@@ -609,10 +609,12 @@ def bench_effnet(D: Dist, steps: int, warmup: int, batch: int | None = None, cpu
     clips_per_s = world * B / (ms * 1e-3)
     act_gbs = B * EFF_ACT_BYTES_PER_CLIP / (ms * 1e-3) / 1e9
     mel_gbs = B * EFF_MEL_BYTES_PER_CLIP / (ms_mel * 1e-3) / 1e9
-    cpu = None
+    cpu = eager = None
+    del model
+    torch.cuda.empty_cache()
     if cpu_baseline and rank == 0 and world == 1:
         cpu = effnet_cpu_baseline()
-    del model
+        eager = effnet_gpu_eager(dev)
     return {
         "workload": "EfficientNet-B0 mel-spectrogram feature extractor, 512 x 5 s clips @16 kHz (BASELINE configs[2]; 512 / n_gpus clips per rank), features [B,1280,4,16]",
         "value": clips_per_s, "unit": "clips/s", "audio_hours_per_s": clips_per_s * EFF_CLIP_SECONDS / 3600.0, "ms_per_step": ms, "steps": steps,
@@ -624,7 +626,7 @@ def bench_effnet(D: Dist, steps: int, warmup: int, batch: int | None = None, cpu
                      "algorithmic_bytes": "35 MB of bf16 activation traffic per 5 s clip (SURVEY 8d)"},
         "kernels": {"melspec": {"ms_per_step": round(ms_mel, 4), "achieved_GBps": mel_gbs, "hbm_frac": mel_gbs / pk["hbm_gbs"],
                                 "algorithmic_bytes_per_clip": EFF_MEL_BYTES_PER_CLIP}},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "gpu_eager_baseline": eager,
     }  # fmt: skip
 
 
@@ -656,6 +658,46 @@ def effnet_cpu_baseline(n_clips: int = 32):
         run(wav[i : i + 8])
     sec = time.perf_counter() - t0
     return {"value": n_clips / sec, "unit": "clips/s", "cores": cores, "kind": kind, "sample": f"{n_clips} x 5 s clips, one pass, {what}, {cores} threads, {sec:.2f} s"}
+
+
+def effnet_gpu_eager(dev, batch: int = 128, steps: int = 3):
+    """The incumbent on the same GPU for the EfficientNet line: the unmodified reference Model (torchaudio / torchvision ops in
+    eager mode) on cuda, fp32 and under bf16 autocast."""
+    import torch
+
+    try:
+        avex = import_reference()
+        if avex is None:
+            raise RuntimeError("baseline/_ref absent")
+        from avex.models.utils.factory import build_model_from_spec
+        from avex.models.utils.registry import get_model_spec
+
+        model = build_model_from_spec(get_model_spec("esp_aves2_effnetb0_all"), "cuda", pretrained=False, return_features_only=True).eval()
+        wav = torch.randn(batch, EFF_CLIP_SECONDS * SAMPLE_RATE, device=dev, generator=torch.Generator(device=dev).manual_seed(4321)) * 0.1
+
+        def timeit():
+            with torch.no_grad():
+                for _ in range(2):
+                    model(wav)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(steps):
+                    model(wav)
+                b.record()
+                torch.cuda.synchronize()
+            return a.elapsed_time(b) / steps
+
+        ms32 = timeit()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ms16 = timeit()
+        out = {"kind": "reference", "what": "unmodified avex efficientnet Model on cuda (AudioProcessor mel + torchvision efficientnet_b0, eager), random init",
+               "batch": batch, "fp32": {"ms_per_batch": ms32, "value": batch / (ms32 * 1e-3)},
+               "autocast_bf16": {"ms_per_batch": ms16, "value": batch / (ms16 * 1e-3)}, "unit": "clips/s"}
+    except Exception as e:  # an OOM or an import problem must not cost the line
+        out = {"unavailable": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -723,11 +765,11 @@ def run_effnet(args):
         sampler.stop()
         line = {"metric": "effnet_b0_feature_throughput", "value": r["value"], "unit": "clips/s", "n_gpus": D.world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong" if D.world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "scaling": "strong" if D.world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": r["workload"], "batch_per_gpu": r["clips_per_rank"], "weights": "random-init, calibrated BatchNorm statistics",
                            "l2": "activations (up to 1.6 GB per layer) exceed the 126 MB L2; no flush needed"},
                 "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "roofline": r["roofline"], "kernels": r["kernels"],
-                "cpu_baseline": r["cpu_baseline"], "clocks": sampler.summary()}  # fmt: skip
+                "cpu_baseline": r["cpu_baseline"], "gpu_eager_baseline": r["gpu_eager_baseline"], "clocks": sampler.summary()}  # fmt: skip
         print(json.dumps(line), flush=True)
     D.close()
 
