@@ -16,7 +16,8 @@ Prints ONE JSON line.
   roofline     the dominant kernel (tcgen05 GEMM): ALGORITHMIC FLOPs / its CUDA-event time inside the step vs the measured
                sustained bf16 peak (`executed_tflops` also counts the 3x K of the split-bf16 front-end GEMMs)
   strong       global batch 256 split over the N ranks (32 clips per rank at N = 8), same step
-  secondary    BASELINE configs[2] (EfficientNet-B0, 512 x 5 s) and configs[4] shape (BEATs, 64 x 60 s, 13 pooled hooks)
+  secondary    BASELINE configs[2] (EfficientNet-B0, 512 x 5 s; with its own e2e, roofline, cpu_baseline and gpu_eager_baseline)
+               and configs[4] shape (BEATs, 64 x 60 s, 13 pooled hooks)
   gpu_eager_baseline   the reference's own torch modules on the SAME GPU (fp32 and autocast-bf16, batch 32): the incumbent
   cpu_baseline the reference's CPU path on this box's host cores, bounded sample (rank 0, N = 1 only)
 `--impl reference` times the UNMODIFIED reference (earthspecies/avex installed under baseline/_ref) on the host cores through its
